@@ -1,0 +1,682 @@
+// sph_api.cu -- host step driver and C ABI (include/sph_b200.h) of libsph_b200.so.
+//
+// Replaces the host half of the reference's simulator.cu (ref: src/simulator.cu:370-546:
+// ctor/dtor, setup(), getPosition(), simulate(), simulateAndTime()).  One stream, the
+// whole step replayed as a CUDA graph, one synchronisation per step (the reference
+// synchronises the device three to four times per step and clears its grid with 10^6
+// one-thread blocks).
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/sph_b200.h"
+#include "sph_kernels.cuh"
+#include "sph_sort.cuh"
+
+using namespace sph;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+enum Stage { kStHash = 0, kStHist, kStSort, kStReorder, kStDensity, kStForce, kStPush, kStOther };
+const char *kStageNames[SPH_STAGE_COUNT] = {"hash",    "histogram",       "sort_passes", "reorder_cellstart",
+                                            "density", "force_integrate", "push",        "other"};
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+}  // namespace
+
+struct sph_sim {
+    SphSettings settings;
+    SphOptions opt;
+    Params p;
+    Thresholds th;
+    DeviceState d;
+    int sm_count = 148;
+    int capacity = 0;
+    int passes = 0;
+    int sorted_buf = 0;
+    cudaStream_t stream = nullptr;
+    float *host_pos = nullptr;  // pinned, 3*n floats, original order
+    bool is_setup = false;
+    bool keys_valid = false;    // d.key matches d.cur_pos
+    bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
+    cudaGraphExec_t graph = nullptr;
+    bool profiling = false;
+    std::vector<EventPair> events;
+    size_t events_used = 0;
+    double stage_ms[SPH_STAGE_COUNT] = {0};
+    int64_t stage_launches[SPH_STAGE_COUNT] = {0};
+    int64_t launches = 0;
+};
+
+namespace {
+
+// ---- instrumentation --------------------------------------------------------------
+void stage_begin(sph_sim *s, int stage) {
+    s->launches++;
+    s->stage_launches[stage]++;
+    if (!s->profiling) return;
+    if (s->events_used == s->events.size()) {
+        EventPair ep;
+        cudaEventCreate(&ep.a);
+        cudaEventCreate(&ep.b);
+        s->events.push_back(ep);
+    }
+    EventPair &ep = s->events[s->events_used];
+    ep.stage = stage;
+    cudaEventRecord(ep.a, s->stream);
+}
+void stage_end(sph_sim *s) {
+    if (!s->profiling) return;
+    cudaEventRecord(s->events[s->events_used].b, s->stream);
+    s->events_used++;
+}
+void profile_collect(sph_sim *s) {  // call after the stream is synchronised
+    for (size_t i = 0; i < s->events_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->events[i].a, s->events[i].b) == cudaSuccess)
+            s->stage_ms[s->events[i].stage] += ms;
+    }
+    s->events_used = 0;
+}
+void sort_before(void *ctx, int st) {
+    stage_begin((sph_sim *)ctx, st == kSortStageHistogram ? kStHist : kStSort);
+}
+void sort_after(void *ctx, int) { stage_end((sph_sim *)ctx); }
+
+// ---- step pieces --------------------------------------------------------------------
+// "build": everything the reference's "Grid construction" bucket covers.
+void enqueue_build(sph_sim *s) {
+    if (!s->keys_valid) {
+        stage_begin(s, kStHash);
+        launch_hash(s->p, s->d, s->stream);
+        stage_end(s);
+        s->keys_valid = true;
+    }
+    SortHooks hooks{s, sort_before, sort_after};
+    s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], s->p.n, s->passes,
+                                     s->d.sort_scratch, s->sm_count, s->stream, &hooks);
+    stage_begin(s, kStReorder);
+    launch_reorder(s->p, s->d, s->sorted_buf, s->sm_count, s->stream);
+    stage_end(s);
+}
+// "update": the reference's "SPH update" bucket.
+void enqueue_update(sph_sim *s) {
+    stage_begin(s, kStDensity);
+    launch_density(s->p, s->d, false, s->stream);
+    stage_end(s);
+    stage_begin(s, kStForce);
+    launch_force_integrate(s->p, s->th, s->d, s->stream);
+    stage_end(s);
+}
+
+int graph_launches_per_step(const sph_sim *s) { return 1 /*hist*/ + s->passes + 3; }
+
+// One timestep on the stream; graph replay when possible.
+int enqueue_step(sph_sim *s) {
+    const bool want_graph = s->opt.use_graph != 2 && !s->profiling;
+    if (want_graph && s->keys_valid) {
+        if (!s->graph) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = s->launches;
+            int64_t sl0[SPH_STAGE_COUNT];
+            memcpy(sl0, s->stage_launches, sizeof(sl0));
+            CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_build(s);
+            enqueue_update(s);
+            CU(cudaStreamEndCapture(s->stream, &g));
+            s->launches = l0;  // capture launches nothing
+            memcpy(s->stage_launches, sl0, sizeof(sl0));
+            CU(cudaGraphInstantiate(&s->graph, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CU(cudaGraphLaunch(s->graph, s->stream));
+        s->launches += graph_launches_per_step(s);
+        s->stage_launches[kStHist] += 1;
+        s->stage_launches[kStSort] += s->passes;
+        s->stage_launches[kStReorder] += 1;
+        s->stage_launches[kStDensity] += 1;
+        s->stage_launches[kStForce] += 1;
+    } else {
+        enqueue_build(s);
+        enqueue_update(s);
+    }
+    s->step_valid = true;
+    return 0;
+}
+
+int sync_stream(sph_sim *s) {
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    if (s->profiling) profile_collect(s);
+    return 0;
+}
+
+void drop_graph(sph_sim *s) {
+    if (s->graph) {
+        cudaGraphExecDestroy(s->graph);
+        s->graph = nullptr;
+    }
+}
+
+float bisect_sqrt_threshold(float target, bool smallest_ge) {
+    // floats are ordered like their bit patterns for positive values
+    uint32_t lo = 0, hi = 0x7f7fffffu;
+    if (smallest_ge) {  // smallest t with sqrtf(t) >= target
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            float t;
+            memcpy(&t, &mid, 4);
+            if (sqrtf(t) >= target) hi = mid; else lo = mid + 1;
+        }
+    } else {            // largest t with sqrtf(t) <= target
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo + 1) / 2;
+            float t;
+            memcpy(&t, &mid, 4);
+            if (sqrtf(t) <= target) lo = mid; else hi = mid - 1;
+        }
+    }
+    float r;
+    memcpy(&r, &lo, 4);
+    return r;
+}
+
+int free_device(sph_sim *s) {
+    DeviceState &d = s->d;
+    cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
+    cudaFree(d.key); cudaFree(d.pairs[0]); cudaFree(d.pairs[1]); cudaFree(d.cell_start);
+    cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(d.out_pos);
+    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts);
+    memset(&d, 0, sizeof(d));
+    if (s->host_pos) cudaFreeHost(s->host_pos);
+    s->host_pos = nullptr;
+    return 0;
+}
+
+// Upload a full state given in ORIGINAL particle order.
+int upload_state(sph_sim *s, const float *pos, const float *vel) {
+    const int n = s->p.n;
+    std::vector<float4> hp((size_t)n), hv((size_t)n);
+    const float box = s->settings.boxDim;
+    for (int i = 0; i < n; ++i) {
+        const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        if (!(x >= 0.f && x < box && y >= 0.f && y < box && z >= 0.f && z < box))
+            return fail(SPH_E_OUT_OF_BOX, "particle %d at (%g, %g, %g) is outside [0, %g)^3", i, x, y,
+                        z, box);
+        uint32_t id = (uint32_t)i;
+        float w;
+        memcpy(&w, &id, 4);
+        hp[i] = make_float4(x, y, z, w);
+        hv[i] = vel ? make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.f)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    CU(cudaMemcpyAsync(s->d.cur_pos, hp.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d.cur_vel, hv.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->keys_valid = false;
+    s->step_valid = false;
+    return 0;
+}
+
+// ids[slot] for the current storage order (from pos.w of `src`)
+int download_ids(sph_sim *s, const float4 *src, std::vector<float4> &buf) {
+    buf.resize((size_t)s->p.n);
+    CU(cudaMemcpyAsync(buf.data(), src, sizeof(float4) * (size_t)s->p.n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+inline uint32_t id_of(const float4 &v) {
+    uint32_t id;
+    memcpy(&id, &v.w, 4);
+    return id;
+}
+
+#define REQUIRE_SETUP(s)                                                  \
+    do {                                                                  \
+        if (!(s)) return fail(SPH_E_INVALID, "null simulator handle");    \
+        if (!(s)->is_setup) return fail(SPH_E_STATE, "sph_setup() has not been called"); \
+        CU(cudaSetDevice((s)->opt.device));                               \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int sph_abi_version(void) { return SPH_B200_ABI_VERSION; }
+const char *sph_last_error(void) { return g_err; }
+const char *sph_stage_name(int stage) {
+    return (stage >= 0 && stage < SPH_STAGE_COUNT) ? kStageNames[stage] : "?";
+}
+
+int sph_create(const SphSettings *settings, sph_sim **out) {
+    return sph_create_ex(settings, nullptr, out);
+}
+
+// ref: simulator.cu:370-375 -- the constructor only records the settings.
+int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **out) {
+    if (!st || !out) return fail(SPH_E_INVALID, "null argument");
+    *out = nullptr;
+    const int nc = (int)st->numCellsPerDim;
+    if (st->numParticles < 0) return fail(SPH_E_INVALID, "numParticles < 0");
+    if (!(st->h > 0.f) || !(st->boxDim > 0.f) || !(st->timestep > 0.f))
+        return fail(SPH_E_INVALID, "h, boxDim and timestep must be positive");
+    if (nc < 1 || nc > 1024 || (float)nc != st->numCellsPerDim)
+        return fail(SPH_E_INVALID, "numCellsPerDim must be an integer in [1, 1024], got %g",
+                    (double)st->numCellsPerDim);
+    sph_sim *s = new (std::nothrow) sph_sim();
+    if (!s) return fail(SPH_E_NOMEM, "out of host memory");
+    s->settings = *st;
+    memset(&s->opt, 0, sizeof(s->opt));
+    if (options) s->opt = *options;
+    if (s->opt.key_mode != SPH_KEY_FLAT && s->opt.key_mode != SPH_KEY_MORTON) {
+        const int bad = s->opt.key_mode;
+        delete s;
+        return fail(SPH_E_INVALID, "unknown key_mode %d", bad);
+    }
+    memset(&s->d, 0, sizeof(s->d));
+    Params &p = s->p;
+    p.n = p.n_owned = st->numParticles;
+    p.nc = nc;
+    p.h = st->h;
+    p.h2 = st->h * st->h;
+    p.vk = st->v_kernel_coeff;
+    p.dk = st->d_kernel_coeff;
+    p.box = st->boxDim;
+    p.hi = st->boxDim - st->h;
+    p.dt = st->timestep;
+    p.key_mode = s->opt.key_mode;
+    if (p.key_mode == SPH_KEY_FLAT) {
+        p.table_size = (uint32_t)nc * nc * nc;
+    } else {
+        int bits = 0;
+        while ((1 << bits) < nc) ++bits;
+        p.table_size = 1u << (3 * bits);
+    }
+    s->passes = sort_passes_for(p.table_size);
+    s->th.r2_eps = bisect_sqrt_threshold(kEps, true);
+    s->th.r2_h = bisect_sqrt_threshold(st->h, false);
+    s->capacity = s->opt.capacity > p.n ? s->opt.capacity : p.n;
+    *out = s;
+    return 0;
+}
+
+void sph_destroy(sph_sim *s) {
+    if (!s) return;
+    if (s->is_setup) {
+        cudaSetDevice(s->opt.device);
+        if (s->stream) cudaStreamSynchronize(s->stream);
+        drop_graph(s);
+        for (auto &ep : s->events) {
+            cudaEventDestroy(ep.a);
+            cudaEventDestroy(ep.b);
+        }
+        free_device(s);
+        if (s->stream) cudaStreamDestroy(s->stream);
+    }
+    delete s;
+}
+
+// ref: simulator.cu:411-460
+int sph_setup(sph_sim *s) {
+    if (!s) return fail(SPH_E_INVALID, "null simulator handle");
+    if (s->is_setup) return fail(SPH_E_STATE, "sph_setup() called twice");
+    const SphSettings &st = s->settings;
+    const int n = s->p.n;
+
+    // -- initial positions, on the host exactly as the reference computes them --
+    std::vector<float> pos((size_t)3 * (n > 0 ? n : 1));
+    if (st.randomInit) {
+        // unseeded glibc rand(): three draws per particle in x, y, z order (ref: 430-437)
+        for (int i = 0; i < n; ++i) {
+            const float x = rand() / (float)RAND_MAX * (st.boxDim - 2.f) + 1.f;
+            const float y = rand() / (float)RAND_MAX * (st.boxDim - 2.f) + 1.f;
+            const float z = rand() / (float)RAND_MAX * (st.boxDim - 2.f) + 1.f;
+            pos[3 * (size_t)i] = x;
+            pos[3 * (size_t)i + 1] = y;
+            pos[3 * (size_t)i + 2] = z;
+        }
+    } else {
+        // 0.9h lattice from (h,h,h), x outer / z inner (ref: 438-453)
+        const float spacing = 0.9f * st.h;
+        const int nx = (int)(floorf((st.boxDim - 2 * st.h) / spacing) + 1);
+        if ((long long)n > (long long)nx * nx * nx)
+            return fail(SPH_E_INVALID,
+                        "grid init: the %d^3 lattice of a boxDim=%g box holds %lld particles, %d "
+                        "requested (the reference leaves the rest uninitialised); scale boxDim / "
+                        "numCellsPerDim",
+                        nx, (double)st.boxDim, (long long)nx * nx * nx, n);
+        int count = 0;
+        for (int x = 0; x < nx && count < n; ++x)
+            for (int y = 0; y < nx && count < n; ++y)
+                for (int z = 0; z < nx && count < n; ++z) {
+                    pos[3 * (size_t)count] = st.h + spacing * x;
+                    pos[3 * (size_t)count + 1] = st.h + spacing * y;
+                    pos[3 * (size_t)count + 2] = st.h + spacing * z;
+                    ++count;
+                }
+    }
+
+    // -- device ---------------------------------------------------------------
+    CU(cudaSetDevice(s->opt.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, s->opt.device));
+    if (prop.major < 10)
+        return fail(SPH_E_INVALID, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    s->opt.device, prop.major, prop.minor);
+    s->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)(s->capacity > 0 ? s->capacity : 1);
+    DeviceState &d = s->d;
+    CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_pos, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_vel, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.key, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.pairs[0], cap * sizeof(uint64_t)));
+    CU(cudaMalloc(&d.pairs[1], cap * sizeof(uint64_t)));
+    CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.pa, cap * sizeof(float2)));
+    CU(cudaMalloc(&d.rho, cap * sizeof(float)));
+    CU(cudaMalloc(&d.out_pos, cap * 3 * sizeof(float)));
+    CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
+    if (s->opt.record_force) CU(cudaMalloc(&d.force, cap * sizeof(float4)));
+    CU(cudaMemset(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
+    CU(cudaMemset(d.rho, 0, cap * sizeof(float)));
+    CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
+    memset(s->host_pos, 0, cap * 3 * sizeof(float));
+    s->is_setup = true;
+    if (n > 0) {
+        int rc = upload_state(s, pos.data(), nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int sph_step(sph_sim *s) {
+    REQUIRE_SETUP(s);
+    if (s->p.n == 0) return 0;
+    int rc = enqueue_step(s);
+    if (rc) return rc;
+    // ref: simulator.cu:478-480 -- blocking copy of every position to the host
+    CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
+                       cudaMemcpyDeviceToHost, s->stream));
+    return sync_stream(s);
+}
+
+// ref: simulator.cu:499-546 -- same wall-clock buckets, launch + sync inside each
+int sph_step_timed(sph_sim *s, SphTimes *times) {
+    REQUIRE_SETUP(s);
+    if (!times) return fail(SPH_E_INVALID, "null times");
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a) {
+        return std::chrono::duration_cast<std::chrono::duration<double>>(clk::now() - a).count();
+    };
+    if (s->p.n > 0) {
+        auto t0 = clk::now();
+        enqueue_build(s);
+        int rc = sync_stream(s);
+        if (rc) return rc;
+        times->buildGrid += secs(t0);
+
+        auto t1 = clk::now();
+        enqueue_update(s);
+        rc = sync_stream(s);
+        if (rc) return rc;
+        times->sphUpdate += secs(t1);
+        s->step_valid = true;
+
+        auto t2 = clk::now();
+        CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
+                           cudaMemcpyDeviceToHost, s->stream));
+        rc = sync_stream(s);
+        if (rc) return rc;
+        times->memcpy += secs(t2);
+    }
+    times->iters += 1;
+    return 0;
+}
+
+int sph_advance(sph_sim *s, int steps) {
+    REQUIRE_SETUP(s);
+    if (steps < 0) return fail(SPH_E_INVALID, "steps < 0");
+    if (s->p.n == 0) return 0;
+    for (int k = 0; k < steps; ++k) {
+        int rc = enqueue_step(s);
+        if (rc) return rc;
+    }
+    return sync_stream(s);
+}
+
+int sph_push(sph_sim *s, int x, int y) {
+    REQUIRE_SETUP(s);
+    if (s->p.n == 0) return 0;
+    if (!s->step_valid) return fail(SPH_E_STATE, "sph_push() needs the cell table of a step that just ran");
+    stage_begin(s, kStPush);
+    launch_push(s->p, s->d, x, y, s->stream);
+    stage_end(s);
+    return sync_stream(s);
+}
+
+const float *sph_positions_host(sph_sim *s) { return s ? s->host_pos : nullptr; }
+
+int sph_readback(sph_sim *s) {
+    REQUIRE_SETUP(s);
+    if (s->p.n == 0) return 0;
+    CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
+                       cudaMemcpyDeviceToHost, s->stream));
+    return sync_stream(s);
+}
+
+int sph_set_state(sph_sim *s, const float *pos, const float *vel) {
+    REQUIRE_SETUP(s);
+    if (!pos) return fail(SPH_E_INVALID, "null positions");
+    if (s->p.n == 0) return 0;
+    return upload_state(s, pos, vel);
+}
+
+int sph_get_state(sph_sim *s, float *pos, float *vel) {
+    REQUIRE_SETUP(s);
+    const int n = s->p.n;
+    if (n == 0) return 0;
+    std::vector<float4> hp, hv;
+    int rc = download_ids(s, s->d.cur_pos, hp);
+    if (rc) return rc;
+    if (vel) {
+        rc = download_ids(s, s->d.cur_vel, hv);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i) {
+        const uint32_t id = id_of(hp[i]);
+        if (id >= (uint32_t)n) return fail(SPH_E_STATE, "corrupt particle id %u at slot %d", id, i);
+        if (pos) { pos[3 * id] = hp[i].x; pos[3 * id + 1] = hp[i].y; pos[3 * id + 2] = hp[i].z; }
+        if (vel) { vel[3 * id] = hv[i].x; vel[3 * id + 1] = hv[i].y; vel[3 * id + 2] = hv[i].z; }
+    }
+    return 0;
+}
+
+int sph_get_keys(sph_sim *s, int key_mode, uint32_t *keys) {
+    REQUIRE_SETUP(s);
+    if (!keys) return fail(SPH_E_INVALID, "null keys");
+    if (key_mode != SPH_KEY_FLAT && key_mode != SPH_KEY_MORTON)
+        return fail(SPH_E_INVALID, "unknown key_mode %d", key_mode);
+    const int n = s->p.n;
+    if (n == 0) return 0;
+    // hash with the requested key form into a temporary, without touching the step's keys
+    uint32_t *tmp = nullptr;
+    CU(cudaMalloc(&tmp, sizeof(uint32_t) * (size_t)n));
+    Params p = s->p;
+    p.key_mode = key_mode;
+    DeviceState d = s->d;
+    d.key = tmp;
+    stage_begin(s, kStHash);
+    launch_hash(p, d, s->stream);
+    stage_end(s);
+    std::vector<uint32_t> hk((size_t)n);
+    cudaError_t e = cudaMemcpyAsync(hk.data(), tmp, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+    int rc = e == cudaSuccess ? sync_stream(s) : fail((int)e, "copy failed: %s", cudaGetErrorString(e));
+    cudaFree(tmp);
+    if (rc) return rc;
+    std::vector<float4> hp;
+    rc = download_ids(s, s->d.cur_pos, hp);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) keys[id_of(hp[i])] = hk[i];
+    return 0;
+}
+
+int sph_get_sorted_index(sph_sim *s, uint32_t *ids, uint32_t *sorted_keys) {
+    REQUIRE_SETUP(s);
+    const int n = s->p.n;
+    if (n == 0) return 0;
+    if (!s->step_valid) return fail(SPH_E_STATE, "no step has run since the state was set");
+    if (ids) {
+        std::vector<float4> hp;
+        int rc = download_ids(s, s->d.srt_pos, hp);
+        if (rc) return rc;
+        for (int i = 0; i < n; ++i) ids[i] = id_of(hp[i]);
+    }
+    if (sorted_keys) {
+        std::vector<uint64_t> pr((size_t)n);
+        CU(cudaMemcpyAsync(pr.data(), s->d.pairs[s->sorted_buf], sizeof(uint64_t) * (size_t)n,
+                           cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < n; ++i) sorted_keys[i] = (uint32_t)(pr[i] >> 32);
+    }
+    return 0;
+}
+
+int sph_get_cell_start(sph_sim *s, uint32_t *start, uint32_t *table_size) {
+    REQUIRE_SETUP(s);
+    if (table_size) *table_size = s->p.table_size;
+    if (!start) return 0;
+    if (!s->step_valid) return fail(SPH_E_STATE, "no step has run since the state was set");
+    CU(cudaMemcpyAsync(start, s->d.cell_start, sizeof(uint32_t) * ((size_t)s->p.table_size + 1),
+                       cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int sph_get_neighbor_counts(sph_sim *s, int32_t *K, int32_t *C) {
+    REQUIRE_SETUP(s);
+    const int n = s->p.n;
+    if (n == 0) return 0;
+    if (!s->d.counts) CU(cudaMalloc(&s->d.counts, sizeof(int32_t) * 2 * (size_t)s->capacity));
+    enqueue_build(s);  // grid of the CURRENT positions; the state itself is untouched
+    stage_begin(s, kStDensity);
+    launch_density(s->p, s->d, true, s->stream);
+    stage_end(s);
+    s->step_valid = false;  // rho/pa/force no longer line up with the sorted slots
+    std::vector<int32_t> h((size_t)2 * n);
+    CU(cudaMemcpyAsync(h.data(), s->d.counts, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    int rc = sync_stream(s);
+    if (rc) return rc;
+    std::vector<float4> hp;
+    rc = download_ids(s, s->d.srt_pos, hp);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t id = id_of(hp[i]);
+        if (K) K[id] = h[i];
+        if (C) C[id] = h[(size_t)n + i];
+    }
+    return 0;
+}
+
+int sph_get_density_pressure_force(sph_sim *s, float *rho, float *prs, float *force) {
+    REQUIRE_SETUP(s);
+    const int n = s->p.n;
+    if (n == 0) return 0;
+    if (!s->step_valid) return fail(SPH_E_STATE, "no step has run since the state was set");
+    if (force && !s->d.force)
+        return fail(SPH_E_STATE, "forces are only kept when SphOptions.record_force is set");
+    std::vector<float4> hp;
+    int rc = download_ids(s, s->d.srt_pos, hp);
+    if (rc) return rc;
+    std::vector<float> hr((size_t)n);
+    std::vector<float2> ha((size_t)n);
+    std::vector<float4> hf;
+    CU(cudaMemcpyAsync(hr.data(), s->d.rho, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(ha.data(), s->d.pa, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (force) {
+        hf.resize((size_t)n);
+        CU(cudaMemcpyAsync(hf.data(), s->d.force, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < n; ++i) {
+        const uint32_t id = id_of(hp[i]);
+        if (rho) rho[id] = hr[i];
+        if (prs) prs[id] = ha[i].x;
+        if (force) { force[3 * id] = hf[i].x; force[3 * id + 1] = hf[i].y; force[3 * id + 2] = hf[i].z; }
+    }
+    return 0;
+}
+
+int sph_get_stats(sph_sim *s, double *ke, double *mean_rho) {
+    REQUIRE_SETUP(s);
+    double h[2] = {0, 0};
+    if (s->p.n > 0) {
+        stage_begin(s, kStOther);
+        launch_stats(s->p, s->d, s->stream);
+        stage_end(s);
+        CU(cudaMemcpyAsync(h, s->d.stats, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+        int rc = sync_stream(s);
+        if (rc) return rc;
+    }
+    if (ke) *ke = h[0];
+    if (mean_rho) *mean_rho = s->p.n ? h[1] / s->p.n : 0.0;
+    return 0;
+}
+
+int sph_profile_enable(sph_sim *s, int on) {
+    REQUIRE_SETUP(s);
+    CU(cudaStreamSynchronize(s->stream));
+    s->profiling = on != 0;
+    s->events_used = 0;
+    return 0;
+}
+
+int sph_profile_read(sph_sim *s, double ms[SPH_STAGE_COUNT], int64_t launches[SPH_STAGE_COUNT], int reset) {
+    REQUIRE_SETUP(s);
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->profiling) profile_collect(s);
+    for (int i = 0; i < SPH_STAGE_COUNT; ++i) {
+        if (ms) ms[i] = s->stage_ms[i];
+        if (launches) launches[i] = s->stage_launches[i];
+        if (reset) {
+            s->stage_ms[i] = 0;
+            s->stage_launches[i] = 0;
+        }
+    }
+    return 0;
+}
+
+int64_t sph_launch_count(sph_sim *s) { return s ? s->launches : 0; }
+int sph_num_particles(sph_sim *s) { return s ? s->p.n : 0; }
+
+}  // extern "C"

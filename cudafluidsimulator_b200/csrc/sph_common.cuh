@@ -1,0 +1,112 @@
+// sph_common.cuh -- shared device-side definitions of the B200 SPH step.
+//
+// Physics constants and rounding rules follow the reference
+// (ref: src/simulator.h:6-12, src/simulator.cu:12-14).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sph {
+
+constexpr float kMass = 0.02f;          // ref: simulator.h:7  MASS
+constexpr float kRestDensity = 1000.f;  // ref: simulator.h:9  REST_DENSITY
+constexpr float kGravity = -9.8f;       // ref: simulator.h:11 GRAVITY
+constexpr float kEps = 1e-4f;           // ref: simulator.cu:14 EPS_F
+constexpr float kPushStrength = 5.f;    // ref: simulator.cu:13 PUSH_STRENGTH
+// GAS_CONSTANT == VISCOSITY == 1 and ELASTICITY == 0.5 are folded in place.
+
+enum KeyMode : int { kKeyFlat = 0, kKeyMorton = 1 };
+
+// Kernel parameters, passed by value (__grid_constant__) -- no __constant__
+// symbol, so several simulators (e.g. one per slab) can coexist in a process.
+struct Params {
+    int n;          // particles in the arrays (owned + ghosts)
+    int n_owned;    // particles this simulator integrates (== n without slabs)
+    int nc;         // cells per dimension (int of the reference's float)
+    float h;        // smoothing length == cell edge
+    float h2;       // h*h, rounded once (ref: simulator.cu:89)
+    float vk;       // v_kernel_coeff = 45/(pi h^6)
+    float dk;       // d_kernel_coeff = 315/(64 pi h^9)
+    float box;      // boxDim
+    float hi;       // boxDim - h, rounded once (ref: simulator.cu:283)
+    float dt;       // timestep
+    int key_mode;   // KeyMode
+    uint32_t table_size;  // number of distinct keys (nc^3 flat, 8^bits Morton)
+};
+
+// ---- cell coordinates and keys ------------------------------------------------
+// ref: simulator.cu:57-76 getGridCell: IEEE divide by h, truncate toward zero.
+// Coordinates are clamped into the table so that no state can index out of
+// bounds (the reference only printf()s).
+__device__ __forceinline__ int cell_coord(float x, const Params &p) {
+    int c = __float2int_rz(__fdiv_rn(x, p.h));
+    return min(max(c, 0), p.nc - 1);
+}
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// ref: simulator.cu:78-82 flattenGridCoord, evaluated in integers (equal to the
+// reference's float evaluation while nc^3 <= 2^24).
+__device__ __forceinline__ uint32_t key_flat(int cx, int cy, int cz, int nc) {
+    return (uint32_t)cx + (uint32_t)nc * ((uint32_t)cy + (uint32_t)nc * (uint32_t)cz);
+}
+
+__device__ __forceinline__ uint32_t key_morton(int cx, int cy, int cz) {
+    return spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t cell_key(int cx, int cy, int cz, int nc) {
+    return MODE == kKeyFlat ? key_flat(cx, cy, cz, nc) : key_morton(cx, cy, cz);
+}
+
+// ref: simulator.cu:85-88 as nvcc contracts it for sm_100a:
+// dy*dy is a rounded product, the dx and dz terms are fused.  Neighbour counts
+// are bit-exact only with exactly this contraction.
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// ---- 27-cell stencil as index runs over the sorted arrays ----------------------
+// cell_start[k] = first sorted slot whose key is >= k (table_size + 1 entries),
+// so the particles of cell k are [cell_start[k], cell_start[k+1]).
+// Flat keys: the three x-neighbours of a row are adjacent keys, so the stencil is
+// 9 contiguous runs.  Morton keys: 27 single-cell runs.
+// Visiting order is the reference's dz, dy, dx loop nest (ref: simulator.cu:163-176).
+template <int MODE, typename F>
+__device__ __forceinline__ void for_each_run(const Params &p, int cx, int cy, int cz,
+                                             const uint32_t *__restrict__ cell_start, F &&f) {
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int zz = cz + dz;
+        if (zz < 0 || zz >= p.nc) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= p.nc) continue;
+            if (MODE == kKeyFlat) {
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, p.nc - 1);
+                const uint32_t row = (uint32_t)p.nc * ((uint32_t)yy + (uint32_t)p.nc * (uint32_t)zz);
+                f(__ldg(cell_start + row + x0), __ldg(cell_start + row + x1 + 1));
+            } else {
+#pragma unroll 1
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = cx + dx;
+                    if (xx < 0 || xx >= p.nc) continue;
+                    const uint32_t m = key_morton(xx, yy, zz);
+                    f(__ldg(cell_start + m), __ldg(cell_start + m + 1));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace sph

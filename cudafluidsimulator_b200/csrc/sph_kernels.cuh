@@ -1,0 +1,41 @@
+// sph_kernels.cuh -- launch interface of the SPH step kernels (sph_kernels.cu).
+#pragma once
+
+#include "sph_common.cuh"
+
+namespace sph {
+
+// Device arrays of one simulator.  "cur" = the state, stored in the order of the
+// last sort; "srt" = the same particles gathered into this step's sorted order.
+// pos.w carries the ORIGINAL particle id (bit pattern), vel.w is unused.
+struct DeviceState {
+    float4 *cur_pos, *cur_vel;   // state (input of the step, overwritten with its output)
+    float4 *srt_pos, *srt_vel;   // sorted copy of the pre-step state
+    uint32_t *key;               // cell key of cur_pos[i]
+    uint64_t *pairs[2];          // (key << 32 | slot) ping-pong buffers of the sort
+    uint32_t *cell_start;        // table_size + 1 entries
+    float2 *pa;                  // per sorted slot: {pressure, -MASS/(2*density)}
+    float *rho;                  // per sorted slot: density
+    float4 *force;               // optional: force of the last step per sorted slot
+    float *out_pos;              // xyz packed, ORIGINAL particle order (host readback source)
+    uint32_t *sort_scratch;
+    double *stats;               // 2 doubles
+    int32_t *counts;             // optional 2*n scratch for K and C
+};
+
+// Predicate thresholds on r^2 that are exactly equivalent to the reference's
+// predicates on r = sqrt_rn(r^2) (ref: simulator.cu:110 `dist < EPS_F`,
+// simulator.cu:125 `dist > h`); computed on the host by bisection over floats.
+struct Thresholds {
+    float r2_eps;  // smallest float t with sqrtf(t) >= EPS_F  => (dist < EPS_F) == (r2 < r2_eps)
+    float r2_h;    // largest  float t with sqrtf(t) <= h      => (dist > h)     == (r2 > r2_h)
+};
+
+void launch_hash(const Params &p, const DeviceState &d, cudaStream_t s);
+void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int sm_count, cudaStream_t s);
+void launch_density(const Params &p, const DeviceState &d, bool counts, cudaStream_t s);
+void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);
+void launch_push(const Params &p, const DeviceState &d, int click_x, int click_y, cudaStream_t s);
+void launch_stats(const Params &p, const DeviceState &d, cudaStream_t s);
+
+}  // namespace sph

@@ -1,0 +1,278 @@
+// sph_sort.cu -- hand-written stable LSD radix sort of (cell key, slot index)
+// pairs for sm_100a: one histogram sweep + one "onesweep" pass per 8-bit digit
+// (chained scan with decoupled look-back, so every pass reads and writes each
+// pair exactly once).
+//
+// Replaces the neighbour-search data structures of the three reference variants
+// (ref: src/simulator.cu:44-55 insertList / 133-147 kernelBuildGrid for the
+// lock-free lists; README.md:5 for index_sort and z_index_sort whose source is
+// not mounted).  Stable => the order is deterministic: (key, position in the
+// array that was sorted).
+//
+// Roofline: HBM.  Algorithmic bytes per pair: histogram 4 (keys read once) and
+// per pass 8 read + 8 written (first pass reads only the 4-byte key, the index
+// is implicit).
+#include "sph_sort.cuh"
+
+namespace sph {
+
+namespace {
+
+constexpr uint32_t kFlagAggregate = 1u << 30;  // tile count published
+constexpr uint32_t kFlagInclusive = 1u << 31;  // inclusive prefix published
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Exclusive scan over the 256 threads of a block; `total` = sum of all inputs.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*8*/,
+                                                             uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t w = s_warp[lane & 7];
+    uint32_t wincl = w;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if ((lane & 7) >= o) wincl += t;
+    }
+    total = __shfl_sync(0xffffffffu, wincl, 7);
+    const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - w, warp);
+    __syncthreads();  // s_warp may be reused by the caller
+    return incl - v + warp_excl;
+}
+
+// ---- histogram of every digit in one sweep over the keys ----------------------
+// Blocked arrangement (16 consecutive keys per thread) with per-thread run
+// aggregation: the array being sorted is last step's sorted order, so the high
+// digits of consecutive keys are almost always equal and would otherwise
+// serialise on one shared-memory counter.
+__global__ void __launch_bounds__(kSortThreads)
+    k_histogram(const uint32_t *__restrict__ keys, int n, int passes, uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t s_hist[kMaxPasses * kRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kSortThreads) s_hist[i] = 0;
+    __syncthreads();
+
+    const int stride = gridDim.x * kSortThreads * 16;
+    for (int base = (blockIdx.x * kSortThreads + threadIdx.x) * 16; base < n; base += stride) {
+        uint32_t k[16];
+        if (base + 16 <= n) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                uint4 q = __ldg(src + v);
+                k[4 * v] = q.x; k[4 * v + 1] = q.y; k[4 * v + 2] = q.z; k[4 * v + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < 16; ++v) k[v] = (base + v < n) ? __ldg(keys + base + v) : 0xffffffffu;
+        }
+        const int valid = min(16, n - base);
+        for (int p = 0; p < passes; ++p) {
+            const int shift = 8 * p;
+            uint32_t run_digit = (k[0] >> shift) & 255u;
+            uint32_t run_len = 1;
+#pragma unroll
+            for (int v = 1; v < 16; ++v) {
+                if (v < valid) {
+                    const uint32_t d = (k[v] >> shift) & 255u;
+                    if (d == run_digit) {
+                        ++run_len;
+                    } else {
+                        atomicAdd(&s_hist[p * kRadix + run_digit], run_len);
+                        run_digit = d;
+                        run_len = 1;
+                    }
+                }
+            }
+            atomicAdd(&s_hist[p * kRadix + run_digit], run_len);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// ---- one onesweep pass ----------------------------------------------------------
+// FIRST: input is the bare key array, the payload (slot index) is implicit.
+// Tile = 4096 consecutive pairs, 8 warps x 512, warp-striped so that every load
+// is a fully coalesced 256-byte (128-byte for FIRST) request and the order of
+// (item, lane) inside a warp is the array order -- needed for stability.
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+    k_onesweep(const uint32_t *__restrict__ keys_in, const uint64_t *__restrict__ pairs_in,
+               uint64_t *__restrict__ pairs_out, int n, int shift,
+               const uint32_t *__restrict__ ghist,  // 256 counts of this digit
+               uint32_t *__restrict__ status,       // tiles x 256, zeroed
+               uint32_t *__restrict__ ticket) {     // zeroed
+    __shared__ uint64_t s_pairs[kSortTile];                 // 32 KB
+    __shared__ uint32_t s_whist[kSortWarps][kRadix];        // 8 KB
+    __shared__ uint32_t s_dstart[kRadix];
+    __shared__ uint32_t s_goff[kRadix];
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Tiles are handed out in launch order: a tile only ever waits on tiles with
+    // a smaller ticket, which are already resident or finished.
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) s_whist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int base = (int)tile * kSortTile;
+    const int tile_valid = min(kSortTile, n - base);
+
+    // -- load -------------------------------------------------------------------
+    uint64_t item[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const int local = warp * (kSortItems * 32) + k * 32 + lane;
+        const int idx = base + local;
+        uint64_t v = ~0ull;  // padding sorts behind everything and is never written
+        if (local < tile_valid) {
+            if (FIRST) v = ((uint64_t)__ldg(keys_in + idx) << 32) | (uint32_t)idx;
+            else v = __ldg(pairs_in + idx);
+        }
+        item[k] = v;
+    }
+
+    // -- stable rank of every item among equal digits of its warp ---------------
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t d = (uint32_t)(item[k] >> (32 + shift)) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s_whist[warp][d];
+            s_whist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = old + below;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // -- per-digit: scan over warps, tile count, look-back -----------------------
+    const int d = tid;  // kSortThreads == kRadix
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = s_whist[w][d];
+        s_whist[w][d] = count;  // exclusive over warps
+        count += c;
+    }
+    uint32_t *my_status = status + (size_t)tile * kRadix + d;
+    st_relaxed(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
+
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan_256(count, s_scan, total);
+    const uint32_t gbase = block_exclusive_scan_256(__ldg(ghist + d), s_scan, total);
+
+    uint32_t excl = 0;
+    if (tile > 0) {
+        int prev = (int)tile - 1;
+        while (true) {
+            const uint32_t v = ld_relaxed(status + (size_t)prev * kRadix + d);
+            if ((v & (kFlagAggregate | kFlagInclusive)) == 0) continue;  // not yet published
+            excl += v & kValueMask;
+            if (v & kFlagInclusive) break;
+            --prev;
+        }
+        st_relaxed(my_status, kFlagInclusive | (excl + count));
+    }
+    s_dstart[d] = dstart;
+    s_goff[d] = gbase + excl - dstart;  // global slot = s_goff[digit] + slot in sorted tile
+    __syncthreads();
+
+    // -- scatter into tile-sorted order in shared memory -------------------------
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t dd = (uint32_t)(item[k] >> (32 + shift)) & 255u;
+        s_pairs[s_dstart[dd] + s_whist[warp][dd] + rank[k]] = item[k];
+    }
+    __syncthreads();
+
+    // -- coalesced runs out to global --------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const int s = k * kSortThreads + tid;
+        if (s < tile_valid) {
+            const uint64_t v = s_pairs[s];
+            const uint32_t dd = (uint32_t)(v >> (32 + shift)) & 255u;
+            pairs_out[s_goff[dd] + (uint32_t)s] = v;
+        }
+    }
+}
+
+}  // namespace
+
+int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
+
+size_t sort_scratch_words(int capacity) {
+    // [ghist: kMaxPasses*256][tickets: kMaxPasses (padded to 64)][status: passes*tiles*256]
+    return (size_t)kMaxPasses * kRadix + 64 + (size_t)kMaxPasses * sort_tiles(capacity) * kRadix;
+}
+
+int sort_passes_for(uint32_t table_size) {
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)table_size) ++bits;
+    return (bits + 7) / 8;
+}
+
+// Enqueues: clear scratch, histogram, `passes` onesweep passes.  Returns the
+// buffer (0 or 1) holding the sorted pairs.  `launches` is incremented per kernel.
+int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, int n, int passes,
+                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks) {
+    const int tiles = sort_tiles(n);
+    uint32_t *ghist = scratch;
+    uint32_t *tickets = scratch + kMaxPasses * kRadix;
+    uint32_t *status = tickets + 64;
+    const size_t used_words = (size_t)kMaxPasses * kRadix + 64 + (size_t)passes * tiles * kRadix;
+    cudaMemsetAsync(scratch, 0, used_words * sizeof(uint32_t), stream);
+
+    if (hooks) hooks->before(hooks->ctx, kSortStageHistogram);
+    int hist_blocks = (n + kSortThreads * 16 - 1) / (kSortThreads * 16);
+    hist_blocks = max(1, min(hist_blocks, sm_count * 8));
+    k_histogram<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, passes, ghist);
+    if (hooks) hooks->after(hooks->ctx, kSortStageHistogram);
+
+    uint64_t *bufs[2] = {pairs0, pairs1};
+    int out = 0;
+    for (int p = 0; p < passes; ++p) {
+        if (hooks) hooks->before(hooks->ctx, kSortStagePass);
+        uint32_t *st = status + (size_t)p * tiles * kRadix;
+        if (p == 0) {
+            k_onesweep<true><<<tiles, kSortThreads, 0, stream>>>(keys, nullptr, bufs[0], n, 0, ghist,
+                                                               st, tickets + p);
+            out = 0;
+        } else {
+            k_onesweep<false><<<tiles, kSortThreads, 0, stream>>>(
+                nullptr, bufs[out], bufs[out ^ 1], n, 8 * p, ghist + p * kRadix, st, tickets + p);
+            out ^= 1;
+        }
+        if (hooks) hooks->after(hooks->ctx, kSortStagePass);
+    }
+    return out;
+}
+
+}  // namespace sph

@@ -1,0 +1,36 @@
+// sph_sort.cuh -- interface of the hand-written onesweep radix sort (sph_sort.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sph {
+
+constexpr int kRadix = 256;                             // 8-bit digits
+constexpr int kSortThreads = 256;                       // == kRadix: thread d owns digit d
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;                          // pairs per thread
+constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 pairs per CTA
+constexpr int kMaxPasses = 4;                           // 32-bit keys
+
+enum { kSortStageHistogram = 0, kSortStagePass = 1 };
+
+// Optional per-kernel instrumentation (CUDA events) supplied by the step driver.
+struct SortHooks {
+    void *ctx;
+    void (*before)(void *ctx, int sort_stage);
+    void (*after)(void *ctx, int sort_stage);
+};
+
+int sort_tiles(int n);
+size_t sort_scratch_words(int capacity);  // uint32 words of scratch for up to `capacity` pairs
+int sort_passes_for(uint32_t table_size); // 8-bit passes needed for keys < table_size
+
+// Sorts (keys[i], i) for i in [0, n) by key, stably.  Pair = key << 32 | index.
+// Enqueues a scratch clear, the histogram kernel and `passes` onesweep kernels on
+// `stream`; returns which of pairs0 / pairs1 (0 / 1) receives the sorted pairs.
+int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, int n, int passes,
+                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks);
+
+}  // namespace sph

@@ -1,0 +1,85 @@
+// simulator.cpp -- `class Simulator` of include/simulator.h as a thin forwarder to the
+// C ABI of libsph_b200.so.  Host-side replacement for ref src/simulator.cu:370-546.
+#include "simulator.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "sph_b200.h"
+
+// The reference passes mouse clicks through two process globals defined in
+// display.cpp:19-20 and declared extern in simulator.cu:16-17.  Weak definitions keep
+// that hand-off working when a display.cpp is linked and let headless programs link
+// without one.
+__attribute__((weak)) bool mouseClicked = false;
+__attribute__((weak)) int2 clickCoords = {0, 0};
+
+static_assert(sizeof(Settings) == sizeof(SphSettings), "Settings layout drifted from the C ABI");
+static_assert(sizeof(Times) == sizeof(SphTimes), "Times layout drifted from the C ABI");
+
+namespace {
+
+SphOptions options_from_env() {
+    SphOptions o;
+    std::memset(&o, 0, sizeof o);
+    if (const char *k = std::getenv("SPH_KEY_MODE"))
+        o.key_mode = (std::strcmp(k, "morton") == 0) ? SPH_KEY_MORTON : SPH_KEY_FLAT;
+    if (const char *d = std::getenv("SPH_DEVICE")) o.device = std::atoi(d);
+    return o;
+}
+
+}  // namespace
+
+Simulator::Simulator(Settings *settings) : impl(NULL), settings(settings) {}
+
+Simulator::~Simulator() {
+    sph_destroy(impl);
+    impl = NULL;
+}
+
+void Simulator::note(int rc, const char *what) {
+    lastStatus = rc;
+    if (rc != 0) fprintf(stderr, "sph: %s failed (%d): %s\n", what, rc, sph_last_error());
+}
+
+void Simulator::setup() {
+    // Settings is read here, not in the constructor, exactly like the reference
+    // (which dereferences the pointer in setup() and on every step).
+    SphSettings s;
+    std::memset(&s, 0, sizeof s);
+    s.randomInit = settings->randomInit ? 1 : 0;
+    s.numParticles = settings->numParticles;
+    s.h = settings->h;
+    s.v_kernel_coeff = settings->v_kernel_coeff;
+    s.d_kernel_coeff = settings->d_kernel_coeff;
+    s.boxDim = settings->boxDim;
+    s.numCellsPerDim = settings->numCellsPerDim;
+    s.timestep = settings->timestep;
+    SphOptions o = options_from_env();
+    int rc = sph_create_ex(&s, &o, &impl);
+    note(rc, "sph_create_ex");
+    if (rc == 0) note(sph_setup(impl), "sph_setup");
+}
+
+const float3 *Simulator::getPosition() {
+    return reinterpret_cast<const float3 *>(sph_positions_host(impl));
+}
+
+void Simulator::simulate() {
+    if (!impl) return;
+    note(sph_step(impl), "sph_step");
+    if (mouseClicked) {  // ref: simulator.cu:482-489
+        note(sph_push(impl, clickCoords.x, clickCoords.y), "sph_push");
+        mouseClicked = false;
+    }
+}
+
+void Simulator::simulateAndTime(Times *times) {
+    if (!impl) return;
+    note(sph_step_timed(impl, reinterpret_cast<SphTimes *>(times)), "sph_step_timed");
+}
+
+void Simulator::moveParticles(int2 mouse_pos) {
+    if (!impl) return;
+    note(sph_push(impl, mouse_pos.x, mouse_pos.y), "sph_push");
+}

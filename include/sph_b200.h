@@ -1,0 +1,158 @@
+/*
+ * sph_b200.h -- C ABI of the B200-native SPH timestep (libsph_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of andrew-sha/CUDAFluidSimulator:
+ * everything the reference's `class Simulator` (ref: src/simulator.h:53-74,
+ * implemented in src/simulator.cu:370-546) does for its two callers
+ * (src/main.cpp:65-76 time mode, src/display.cpp:35-64 free mode) is reachable
+ * through these entry points with plain pointers and sizes.  include/simulator.h
+ * is the source-compatible C++ class that forwards to them.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a cudaError_t (>0) for CUDA failures or a
+ *     negative SPH_E_* code; sph_last_error() gives a thread-local message.
+ *     (The reference checks nothing -- ref: SURVEY 5.3 -- so there is no error
+ *     behaviour to mirror; callers that ignore the int get reference behaviour.)
+ *   - particle arrays crossing the boundary are xyz-interleaved float32,
+ *     3*numParticles values, indexed by ORIGINAL particle id exactly like the
+ *     reference's `position[i]` (ref: simulator.cu:317, 407-409), no matter how
+ *     the library orders particles internally.
+ *   - there is no CPU fallback: without a CUDA device every call that needs one
+ *     fails with the CUDA error.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_B200_ABI_VERSION 1
+
+/* Layout-identical to the reference's `struct Settings` (ref: simulator.h:19-31,
+ * sizeof == 32: bool at 0, int at 4, six floats from 8), so a `Settings *` may be
+ * passed directly. */
+typedef struct SphSettings {
+    uint8_t randomInit; /* ref: bool randomInit */
+    uint8_t _pad[3];
+    int32_t numParticles;
+    float h;
+    float v_kernel_coeff;
+    float d_kernel_coeff;
+    float boxDim;
+    float numCellsPerDim; /* a float in the reference */
+    float timestep;
+} SphSettings;
+
+/* Layout-identical to the reference's `struct Times` (ref: times.h:5-10). */
+typedef struct SphTimes {
+    double buildGrid; /* hash + radix sort + cell ranges + reorder, seconds */
+    double sphUpdate; /* density/pressure + force/integrate, seconds        */
+    double memcpy;    /* device -> host position copy, seconds              */
+    int32_t iters;
+} SphTimes;
+
+typedef struct sph_sim sph_sim; /* opaque simulator handle */
+
+enum { /* cell-key form used for the sort (north_star item 1) */
+    SPH_KEY_FLAT = 0,  /* x + n*(y + n*z)          (ref: simulator.cu:78-82) */
+    SPH_KEY_MORTON = 1 /* 3-D bit interleave, x in bit 0 (README.md:5)       */
+};
+
+enum {
+    SPH_E_INVALID = -1,   /* bad argument / bad settings                       */
+    SPH_E_STATE = -2,     /* call order (e.g. step before setup)               */
+    SPH_E_NOMEM = -3,     /* host allocation failed                            */
+    SPH_E_OUT_OF_BOX = -4 /* a particle lies outside [0, boxDim)^3 (the
+                             reference printf()s and indexes out of bounds,
+                             ref: simulator.cu:60-73)                           */
+};
+
+/* Extra, additive knobs; zero-initialise for reference behaviour. */
+typedef struct SphOptions {
+    int32_t device;       /* CUDA device ordinal (default 0)                     */
+    int32_t key_mode;     /* SPH_KEY_FLAT (default) or SPH_KEY_MORTON            */
+    int32_t record_force; /* keep per-particle force of the last step for
+                             sph_get_density_pressure_force()                    */
+    int32_t use_graph;    /* 1 (default when 0 is passed via sph_create): replay
+                             the step as a CUDA graph; 2 = plain launches        */
+    int32_t capacity;     /* >= numParticles; room for ghost/migrated particles
+                             in slab mode (0 = numParticles)                     */
+    /* slab decomposition (multi-GPU); z_cell_lo == z_cell_hi == 0 => whole box  */
+    int32_t z_cell_lo;    /* first owned cell layer along z                      */
+    int32_t z_cell_hi;    /* one past the last owned cell layer                  */
+    int32_t reserved[9];
+} SphOptions;
+
+/* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */
+int sph_create(const SphSettings *settings, sph_sim **out);
+int sph_create_ex(const SphSettings *settings, const SphOptions *options, sph_sim **out);
+void sph_destroy(sph_sim *sim);
+/* Allocates device state and initialises particles exactly as the reference
+ * does (random: unseeded glibc rand(), 3 draws/particle; grid: 0.9h lattice,
+ * x outer / z inner), then uploads.  ref: simulator.cu:411-460 */
+int sph_setup(sph_sim *sim);
+
+/* --- per-timestep advance ----------------------------------------------------
+ * sph_step: one timestep + blocking device->host copy of all positions, i.e.
+ * Simulator::simulate() without the mouse hand-off (ref: simulator.cu:462-497).
+ * sph_step_timed: same, accumulating the reference's three wall-clock buckets,
+ * i.e. Simulator::simulateAndTime() (ref: simulator.cu:499-546).
+ * sph_advance: `steps` timesteps without any host readback (device-resident
+ * benchmarking; no reference equivalent). */
+int sph_step(sph_sim *sim);
+int sph_step_timed(sph_sim *sim, SphTimes *times);
+int sph_advance(sph_sim *sim, int steps);
+/* Mouse push applied to the cell grid of the step that just ran, i.e. what
+ * simulate() does when display.cpp set mouseClicked (ref: simulator.cu:329-367,
+ * 482-489).  x,y are window pixels. */
+int sph_push(sph_sim *sim, int x, int y);
+
+/* --- position readback (ref: Simulator::getPosition, simulator.cu:407-409) ---
+ * Pinned host buffer owned by the simulator, 3*numParticles floats in original
+ * particle order, refreshed by sph_step / sph_step_timed / sph_readback. */
+const float *sph_positions_host(sph_sim *sim);
+int sph_readback(sph_sim *sim);
+
+/* --- state injection / parity hooks (test plumbing) ---------- */
+int sph_set_state(sph_sim *sim, const float *pos, const float *vel /* may be NULL => 0 */);
+int sph_get_state(sph_sim *sim, float *pos, float *vel);
+/* cell keys of the CURRENT positions, original particle order */
+int sph_get_keys(sph_sim *sim, int key_mode, uint32_t *keys);
+/* order of the LAST step's sort: ids[s] = original id at sorted slot s,
+ * sorted_keys[s] its key (either may be NULL) */
+int sph_get_sorted_index(sph_sim *sim, uint32_t *ids, uint32_t *sorted_keys);
+/* cell table of the LAST step: start[k] = first sorted slot with key >= k,
+ * table_size+1 entries; *table_size receives the number of keys */
+int sph_get_cell_start(sph_sim *sim, uint32_t *start, uint32_t *table_size);
+/* K[i] = neighbours with !(r^2 > h^2) (self included), C[i] = candidates in the
+ * 27-cell stencil, for the CURRENT positions, original order */
+int sph_get_neighbor_counts(sph_sim *sim, int32_t *K, int32_t *C);
+/* density / pressure / force the LAST step computed (from its pre-step
+ * positions), original order; force needs options.record_force */
+int sph_get_density_pressure_force(sph_sim *sim, float *rho, float *prs, float *force);
+/* kinetic energy 0.5*m*|v|^2 summed, and mean density of the last step */
+int sph_get_stats(sph_sim *sim, double *kinetic_energy, double *mean_density);
+
+/* --- measurement -------------------------------------------------------------
+ * Per-kernel CUDA-event times (ms, summed since the last reset) for the stages
+ * hash, histogram, sort passes, reorder+cell ranges, density, force+integrate.
+ * Enabling adds event records around every launch (and disables the graph). */
+#define SPH_STAGE_COUNT 8
+int sph_profile_enable(sph_sim *sim, int on);
+int sph_profile_read(sph_sim *sim, double ms[SPH_STAGE_COUNT], int64_t launches[SPH_STAGE_COUNT],
+                     int reset);
+const char *sph_stage_name(int stage);
+/* total kernel launches issued by this simulator so far */
+int64_t sph_launch_count(sph_sim *sim);
+int sph_num_particles(sph_sim *sim);
+
+const char *sph_last_error(void);
+int sph_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */
