@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the SPH timestep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 16m_grid|1m_random|10k_grid]
+                    [--key flat|morton] [--impl b200|reference]
+
+One "step" = one full timestep (hash, radix sort, cell ranges, reorder, density/pressure,
+force + integrate) of every particle.  Prints ONE JSON line (rank 0).
+
+  value        N*K / device time of K graph-replayed steps, state resident in HBM
+               (CUDA events on the simulator's own stream, max over ranks)
+  e2e          the same K steps through the reference-facing call sph_step()
+               (== Simulator::simulate()): every step ends with the blocking
+               device->host copy of all N positions into the simulator's pinned host
+               buffer, exactly the reference's per-step contract (ref: simulator.cu:478-480).
+               The path has no per-step host input (state is device-resident by the
+               reference's own design, uploaded once in setup()), so h2d is 0 per step and
+               the one-off setup upload is reported as setup_h2d_bytes.
+  roofline     dominant kernel, measured live with CUDA events around every launch in a
+               separate profiled pass (plain launches) right after the timed region
+  cpu_baseline serial C port of the step (oracle/sph_oracle.c), 1 thread, bounded sample
+  --impl reference   the reference's own implementation: its unmodified CUDA code
+               (oracle/_ref/libsph_ref.so) on the same GPU -- the reference ships no CPU
+               path; falls back to the serial C port if that library
+               is absent.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: 16M particles, grid init, scaled box
+    "16m_grid": dict(n=16_000_000, randomInit=False, boxDim=25.6, numCellsPerDim=256.0),
+    # BASELINE.json configs[1]: 1M particles, random init, reference box
+    "1m_random": dict(n=1_000_000, randomInit=True, boxDim=10.0, numCellsPerDim=100.0),
+    # BASELINE.json configs[0]: ./sph -n 10000 -i grid -m time
+    "10k_grid": dict(n=10_000, randomInit=False, boxDim=10.0, numCellsPerDim=100.0),
+}
+
+
+# ---- clocks during the timed region --------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+        0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [],
+                    "note": "nvml unavailable" if not self.nv else "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+# ---- CPU baseline: the serial C port on a bounded sample -----------------------------
+def cpu_baseline(wl, budget_s=20.0):
+    from oracle.oracle import CpuOracle
+    o = CpuOracle(wl["n"], boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"],
+                  randomInit=wl["randomInit"])
+    o.setup()
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        o.step()
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 100 or el + el / steps > 1.5 * budget_s:
+            break
+    return {"value": wl["n"] * steps / el, "unit": "particle-updates/s", "cores": 1, "kind": "port",
+            "sample": f"first {steps} step(s) of the same workload ({wl['n']} particles) from its initial "
+                      f"state, {el:.1f} s on one host thread; early steps are the sparsest of the run, "
+                      f"which favours the CPU",
+            "host_cores_available": os.cpu_count()}
+
+
+# ---- the reference arm ------------------------------------------------------------------
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    from oracle.oracle import REF_SO
+    line = {"impl": "reference", "metric": "particle-updates/s", "unit": "particle-updates/s",
+            "n_gpus": args.gpus, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, **{k: wl[k] for k in ("n", "boxDim", "numCellsPerDim")},
+                       "init": "random(glibc rand seed 1)" if wl["randomInit"] else "grid lattice"}}
+    budget = 150.0
+    if REF_SO.exists():
+        import torch
+        from oracle.oracle import RefSim
+        torch.cuda.init()
+        ref = RefSim(wl["n"], boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"],
+                     randomInit=wl["randomInit"])
+        for _ in range(args.warmup):
+            ref.step_timed()
+        ref.buckets[0] = ref.buckets[1] = ref.buckets[2] = 0.0
+        torch.cuda.synchronize()
+        steps, t0 = 0, time.perf_counter()
+        while steps < args.steps and time.perf_counter() - t0 < budget:
+            ref.step_timed()     # Simulator::simulateAndTime(): its own three wall-clock buckets
+            steps += 1
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        b = list(ref.buckets)
+        dev = b[0] + b[1]
+        line.update({
+            "value": wl["n"] * steps / dev, "steps": steps, "ms_per_step": 1e3 * dev / steps,
+            "cpu_baseline": {"value": wl["n"] * steps / dev, "unit": "particle-updates/s", "cores": 0,
+                             "kind": "reference",
+                             "sample": f"{steps} steps of the reference's unmodified CUDA code on this GPU "
+                                       "(the reference has no CPU implementation); value = N*steps / "
+                                       "(Grid construction + SPH update buckets of simulateAndTime)"},
+            "e2e": {"value": wl["n"] * steps / wall, "unit": "particle-updates/s",
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "all-in wall clock of simulateAndTime incl. its per-step D2H of N*12 B into "
+                            "pageable memory and its grid reset"},
+            "reference_buckets_s": {"buildGrid": b[0], "sphUpdate": b[1], "memcpy": b[2]},
+        })
+        ref.close()
+    else:
+        cb = cpu_baseline(wl, budget_s=60.0)
+        cb["kind"] = "port"
+        line.update({"value": cb["value"], "steps": args.steps, "ms_per_step": None, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0},
+                     "note": "oracle/_ref/libsph_ref.so absent: serial C port used"})
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -------------------------------------------------------------------------
+def flops_per_particle(C, K):
+    # density 9C+6K+3, force 9C+32K, integrate 30
+    return (9 * C + 6 * K + 3), (9 * C + 32 * K), 30.0
+
+
+def run_ours(args, wl, rank, local_rank, world):
+    import torch
+    import cudafluidsimulator_b200 as sph
+
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.init()
+    key_mode = sph.SPH_KEY_MORTON if args.key == "morton" else sph.SPH_KEY_FLAT
+    n = wl["n"]
+    st = sph.Settings(numParticles=n, randomInit=wl["randomInit"], boxDim=wl["boxDim"],
+                      numCellsPerDim=wl["numCellsPerDim"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)  # -i random: the reference's unseeded glibc state, reproducibly
+
+    # -- device-resident timed region ------------------------------------------------
+    t_setup = time.perf_counter()
+    sim = sph.Simulator(st, key_mode=key_mode, device=local_rank)
+    sim.setup()
+    setup_s = time.perf_counter() - t_setup
+    sim.advance(args.warmup)
+    l0 = sim.launch_count
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ms = sim.advance_timed(args.steps)
+        barrier()
+    launches = sim.launch_count - l0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # -- stage times + neighbour statistics for the rooflines (state after the timed region)
+    K, C = sim.get_neighbor_counts()
+    meanK, meanC = float(K.mean()), float(C.mean())
+    prof_steps = max(3, min(10, args.steps))
+    sim.profile_enable(True)
+    sim.profile_read(reset=True)
+    sim.advance(prof_steps)
+    prof = sim.profile_read(reset=True)
+    sim.profile_enable(False)
+    stage_ms = {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]}
+    sim.close()
+
+    # -- e2e: same workload through sph_step() with the per-step D2H of positions --------
+    libc.srand(1)
+    sim = sph.Simulator(st, key_mode=key_mode, device=local_rank)
+    sim.setup()
+    for _ in range(args.warmup):
+        sim.simulate()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.simulate()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(sim.getPosition()[:: max(1, n // 1000)].sum())
+    sim.close()
+
+    if rank != 0:
+        return
+    hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
+    clk = clocks.summary()
+    f_den, f_force, f_int = flops_per_particle(meanC, meanK)
+    passes = 3
+    bytes_stage = {  # algorithmic bytes per particle
+        "hash": 20, "histogram": 4, "sort_passes": 4 + 8 + 16 * (passes - 1),
+        "reorder_cellstart": 8 + 32 + 32 + 4 * (wl["numCellsPerDim"] ** 3) / n,
+        "density": 16 + 12, "force_integrate": 16 + 16 + 8 + 4 + 16 + 16 + 4 + 12,
+    }
+    flops_stage = {"density": f_den, "force_integrate": f_force + f_int}
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak_tflops = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    stages = {}
+    for name, t_ms in stage_ms.items():
+        e = {"ms": round(t_ms, 4), "share": round(t_ms / sum(stage_ms.values()), 4)}
+        if name in bytes_stage:
+            e["algorithmic_GBps"] = round(bytes_stage[name] * n / (t_ms * 1e-3) / 1e9, 1)
+            e["hbm_frac"] = round(e["algorithmic_GBps"] / hbm_peak, 4)
+        if name in flops_stage:
+            e["algorithmic_TFLOPs"] = round(flops_stage[name] * n / (t_ms * 1e-3) / 1e12, 3)
+            e["fp32_frac"] = round(e["algorithmic_TFLOPs"] / fp32_peak_tflops, 4)
+        stages[name] = e
+    dom = max(stage_ms, key=stage_ms.get)
+    d = stages[dom]
+    if dom in flops_stage:
+        roof = {"kernel": dom, "bound": "fp32", "achieved": d["algorithmic_TFLOPs"], "peak": round(fp32_peak_tflops, 2),
+                "unit": "TFLOP/s", "frac": d["fp32_frac"], "traffic": None,
+                "peak_source": f"SMs*128 lanes*2*clocks.max.sm ({sm_count} SMs, {sm_max_mhz:.0f} MHz from "
+                               f"MEASURED_PEAKS.json, {peak_kind}); no tensor cores on this path",
+                "flops_per_particle": round(flops_stage[dom], 1), "mean_candidates_C": round(meanC, 2),
+                "mean_neighbours_K": round(meanK, 2), "hbm_GBps": d.get("algorithmic_GBps"),
+                "hbm_frac": d.get("hbm_frac")}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": d["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"}
+
+    line = {
+        "metric": "particle-updates/s", "value": value, "unit": "particle-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "n_per_gpu": n, "boxDim": wl["boxDim"],
+                   "numCellsPerDim": wl["numCellsPerDim"], "h": 0.1, "timestep": 0.01,
+                   "init": "random(glibc rand seed 1)" if wl["randomInit"] else "grid lattice (dam-break column)",
+                   "key": args.key, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": "each step consumes the previous step's output (no repeated input); "
+                         f"working set {n * 108 / 1e6:.0f} MB vs 126 MB L2"},
+        "clocks": clk,
+        "e2e": {"value": world * n * args.steps / e2e_s, "unit": "particle-updates/s",
+                "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": n * 12, "setup_h2d_bytes": n * 32, "setup_s": round(setup_s, 3),
+                "api": "sph_step() == Simulator::simulate(): step + blocking D2H of all positions into pinned host memory",
+                "checksum": checksum},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "stages": stages,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="16m_grid", choices=list(WORKLOADS))
+    ap.add_argument("--key", default="flat", choices=["flat", "morton"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, local_rank, world = dist_env()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_ours(args, wl, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

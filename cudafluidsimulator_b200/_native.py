@@ -59,6 +59,7 @@ SYMBOLS = {
     "sph_step": (C.c_int, [_P]),
     "sph_step_timed": (C.c_int, [_P, C.POINTER(SphTimes)]),
     "sph_advance": (C.c_int, [_P, C.c_int]),
+    "sph_advance_timed": (C.c_int, [_P, C.c_int, _F]),
     "sph_push": (C.c_int, [_P, C.c_int, C.c_int]),
     "sph_positions_host": (_F, [_P]),
     "sph_readback": (C.c_int, [_P]),

@@ -7,7 +7,7 @@ travel with the repo snapshot to the GPU box).
 Targets
     cudafluidsimulator_b200/libsph_b200.so   CUDA kernels + C ABI (include/sph_b200.h), sm_100a only
     cudafluidsimulator_b200/sph              drop-in `./sph -n -i -m` CLI (host C++ over the C ABI)
-    oracle/liboracle.so, oracle/_ref/...     test infrastructure (see oracle/Makefile)
+    oracle/ (via its Makefile)               test infrastructure only
 """
 from __future__ import annotations
 

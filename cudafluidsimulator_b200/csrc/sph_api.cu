@@ -475,6 +475,24 @@ int sph_advance(sph_sim *s, int steps) {
     return sync_stream(s);
 }
 
+int sph_advance_timed(sph_sim *s, int steps, float *ms) {
+    REQUIRE_SETUP(s);
+    if (steps < 0 || !ms) return fail(SPH_E_INVALID, "bad argument");
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, s->stream));
+    int rc = 0;
+    for (int k = 0; k < steps && rc == 0 && s->p.n > 0; ++k) rc = enqueue_step(s);
+    cudaEventRecord(b, s->stream);
+    if (rc == 0) rc = sync_stream(s);
+    *ms = 0.f;
+    if (rc == 0) cudaEventElapsedTime(ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return rc;
+}
+
 int sph_push(sph_sim *s, int x, int y) {
     REQUIRE_SETUP(s);
     if (s->p.n == 0) return 0;

@@ -130,6 +130,12 @@ class Simulator:
     def advance(self, steps: int) -> None:
         N.check(self._lib.sph_advance(self._h, int(steps)))
 
+    def advance_timed(self, steps: int) -> float:
+        """Device milliseconds (CUDA events on the simulator's stream) for `steps` steps."""
+        ms = C.c_float()
+        N.check(self._lib.sph_advance_timed(self._h, int(steps), C.byref(ms)))
+        return float(ms.value)
+
     def readback(self) -> np.ndarray:
         N.check(self._lib.sph_readback(self._h))
         return self.getPosition()

@@ -105,6 +105,9 @@ int sph_setup(sph_sim *sim);
 int sph_step(sph_sim *sim);
 int sph_step_timed(sph_sim *sim, SphTimes *times);
 int sph_advance(sph_sim *sim, int steps);
+/* sph_advance bracketed by CUDA events on the simulator's own stream; *ms receives
+ * the device time of the `steps` timesteps (measurement helper for bench.py). */
+int sph_advance_timed(sph_sim *sim, int steps, float *ms);
 /* Mouse push applied to the cell grid of the step that just ran, i.e. what
  * simulate() does when display.cpp set mouseClicked (ref: simulator.cu:329-367,
  * 482-489).  x,y are window pixels. */

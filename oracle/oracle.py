@@ -57,7 +57,7 @@ class CpuOracle:
         L.oracle_sort_order.restype = C.c_int
         sp = C.POINTER(OracleSettings)
         L.oracle_density.argtypes = [_F, C.c_int, sp, _F, _F, _I, _I]
-        L.oracle_forces.argtypes = [_F, _F, _F, _F, C.c_int, sp, _F]
+        L.oracle_forces.argtypes = [_F, _F, _F, _F, C.c_int, sp, _F, C.c_int]
         L.oracle_integrate.argtypes = [_F, _F, _F, _F, C.c_int, sp]
         L.oracle_step.argtypes = [_F, _F, _F, _F, _F, C.c_int, sp]
         L.oracle_push.argtypes = [_F, _F, C.c_int, sp, C.c_int, C.c_int]
@@ -141,7 +141,7 @@ class CpuOracle:
             raise RuntimeError(f"oracle_density failed: {rc}")
         return rho, prs, K, Cn
 
-    def forces(self, pos, vel, rho, prs):
+    def forces(self, pos, vel, rho, prs, abs_mode=False):
         pos = np.ascontiguousarray(pos, np.float32)
         vel = np.ascontiguousarray(vel, np.float32)
         rho = np.ascontiguousarray(rho, np.float32)
@@ -151,7 +151,7 @@ class CpuOracle:
         s = OracleSettings.from_buffer_copy(self.s)
         s.numParticles = n
         rc = self.L.oracle_forces(_p(pos, C.c_float), _p(vel, C.c_float), _p(rho, C.c_float),
-                                  _p(prs, C.c_float), n, C.byref(s), _p(f, C.c_float))
+                                  _p(prs, C.c_float), n, C.byref(s), _p(f, C.c_float), int(abs_mode))
         if rc:
             raise RuntimeError(f"oracle_forces failed: {rc}")
         return f

@@ -1,0 +1,270 @@
+"""GPU suite: the CUDA path (libsph_b200.so through its C ABI) against the CPU oracle
+on identical seeded states.
+
+Bars (north_star): cell keys, sorted order and neighbour counts bit-exact; single-step
+density, force and position within a stated FP32 relative tolerance; multi-step
+aggregates within a stated bound.
+
+  integers (keys, order, cell table, K, C)            bit-exact
+  density, pressure                                   bit-exact vs the oracle (same
+                                                      arithmetic, same visiting order)
+  force            |dF| <= 1e-5 * max(|F|, sum|terms|) per component
+  position         rtol 1e-5 / atol 1e-6 after one step
+"""
+import numpy as np
+import pytest
+
+import cudafluidsimulator_b200 as sph
+from conftest import (compressed_state, developed_state, force_tolerance, lattice_state,
+                      random_state)
+from oracle.oracle import CpuOracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL_POS = 1e-5
+RTOL_F = 1e-5
+
+
+def make(n, key_mode=sph.SPH_KEY_FLAT, **kw):
+    s = sph.Settings(numParticles=n, **kw)
+    sim = sph.Simulator(s, key_mode=key_mode, record_force=True)
+    sim.setup()
+    return sim
+
+
+STATES = {
+    "lattice_sheet_10k": lambda: lattice_state(10000),
+    "lattice_3d_40k": lambda: lattice_state(109 * 109 * 3 + 777),
+    "random_30k": lambda: random_state(30000, seed=7),
+    "random_moving_20k": lambda: random_state(20000, seed=8, lo=2.0, hi=5.0, vel_scale=2.0),
+    "compressed_6k": lambda: compressed_state(6000),
+    "developed_grid_8k_60": lambda: developed_state(8000, 60),
+    "ragged_4097": lambda: random_state(4097, seed=9),
+    "single": lambda: (np.float32([[5, 5, 5]]), np.float32([[0.3, 0, 0]])),
+    "two_coincident": lambda: (np.float32([[5, 5, 5], [5, 5, 5]]), np.zeros((2, 3), np.float32)),
+    "walls": lambda: (np.float32([[0.1, 0.1, 0.1], [9.9, 9.9, 9.9], [0.1, 9.9, 5.0], [0.0, 0.0, 0.0],
+                                  [9.99, 9.99, 9.99]]),
+                      np.float32([[-1, -1, -1], [1, 1, 1], [-5, 5, 0], [0, 0, 0], [2, 2, 2]])),
+}
+
+
+@pytest.mark.parametrize("name", list(STATES))
+@pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
+def test_keys_order_counts_bit_exact(name, mode):
+    pos, vel = STATES[name]()
+    n = len(pos)
+    o = CpuOracle(n)
+    sim = make(n, key_mode=mode)
+    sim.set_state(pos, vel)
+    cells, ff, fi, mo = o.keys(pos)
+    # (1) hashing, both forms, regardless of the sort's key mode
+    np.testing.assert_array_equal(sim.get_keys(sph.SPH_KEY_FLAT), fi.astype(np.uint32))
+    np.testing.assert_array_equal(sim.get_keys(sph.SPH_KEY_MORTON), mo)
+    # (2) neighbour and candidate counts
+    rho, prs, K, C = o.density(pos)
+    Kg, Cg = sim.get_neighbor_counts()
+    np.testing.assert_array_equal(Kg, K)
+    np.testing.assert_array_equal(Cg, C)
+    # (3) sorted order == stable sort by key of the original order; cell table
+    sim.simulate()
+    ids, skeys = sim.get_sorted_index()
+    keys = fi.astype(np.uint32) if mode == sph.SPH_KEY_FLAT else mo
+    table = 100 ** 3 if mode == sph.SPH_KEY_FLAT else 128 ** 3
+    order, start = o.sort_order(keys, table)
+    np.testing.assert_array_equal(ids, order.astype(np.uint32))
+    np.testing.assert_array_equal(skeys, keys[order])
+    np.testing.assert_array_equal(sim.get_cell_start(), start.astype(np.uint32))
+    sim.close()
+
+
+@pytest.mark.parametrize("name", list(STATES))
+@pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
+def test_single_step_density_force_position(name, mode):
+    pos, vel = STATES[name]()
+    n = len(pos)
+    o = CpuOracle(n)
+    o.set_state(pos, vel)
+    o.step()
+    sim = make(n, key_mode=mode)
+    sim.set_state(pos, vel)
+    sim.simulate()
+    rho, prs, f = sim.get_density_pressure_force()
+    if mode == sph.SPH_KEY_FLAT:
+        # same arithmetic and same visiting order as the oracle: bit-exact
+        np.testing.assert_array_equal(rho, o.rho)
+        np.testing.assert_array_equal(prs, o.prs)
+    else:
+        np.testing.assert_allclose(rho, o.rho, rtol=2e-6, atol=0)
+        np.testing.assert_allclose(prs, o.prs, rtol=0, atol=2e-6 * float(o.rho.max()))
+    tol = force_tolerance(o, pos, vel, o.rho, o.prs, rel=RTOL_F)
+    err = np.abs(f - o.force)
+    assert np.all(err <= tol), f"force: worst excess {np.max(err / tol):.3g}x tolerance"
+    p1, v1 = sim.get_state()
+    np.testing.assert_allclose(p1, o.pos, rtol=RTOL_POS, atol=1e-6)
+    # velocity inherits the force tolerance: dv = dt * dF / rho
+    vtol = 0.01 * tol / o.rho[:, None] + 1e-5 * np.abs(o.vel) + 1e-6
+    flipped = (np.abs(o.vel) < 2e-4) | (np.abs(v1) < 2e-4)  # |v| < 1e-4 -> 0 is discontinuous
+    assert np.all((np.abs(v1 - o.vel) <= vtol) | flipped)
+    # the host readback is the reference's position[i], original order
+    np.testing.assert_array_equal(sim.getPosition(), p1)
+    sim.close()
+
+
+def test_first_step_free_fall_bit_exact():
+    pos, vel = lattice_state(20000)
+    o = CpuOracle(len(pos))
+    o.set_state(pos, vel)
+    o.step()
+    sim = make(len(pos))
+    sim.simulate()  # setup() itself produced the lattice (ref: simulator.cu:438-453)
+    np.testing.assert_array_equal(sim.getPosition(), o.pos)
+    sim.close()
+
+
+def test_setup_random_init_matches_reference_rand():
+    import ctypes
+    ctypes.CDLL("libc.so.6").srand(1)  # the reference's unseeded state
+    sim = make(1000, randomInit=True)
+    o = CpuOracle(1000, randomInit=True)
+    o.setup()
+    p, v = sim.get_state()
+    np.testing.assert_array_equal(p, o.pos)
+    assert not v.any()
+    sim.close()
+
+
+@pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
+def test_sort_is_stable_across_steps(mode):
+    """After step k the storage order is step k's sorted order; step k+1 must be a
+    STABLE sort of that order by the new keys (ties keep the previous order)."""
+    pos, vel = random_state(50000, seed=11, lo=1.0, hi=4.0, vel_scale=3.0)
+    sim = make(len(pos), key_mode=mode)
+    sim.set_state(pos, vel)
+    sim.simulate()
+    prev_ids, _ = sim.get_sorted_index()
+    for _ in range(3):
+        keys_now = sim.get_keys(mode)                  # by original id, current positions
+        sim.simulate()
+        ids, skeys = sim.get_sorted_index()
+        k_in_storage_order = keys_now[prev_ids]
+        expect = prev_ids[np.argsort(k_in_storage_order, kind="stable")]
+        np.testing.assert_array_equal(ids, expect)
+        np.testing.assert_array_equal(skeys, np.sort(k_in_storage_order))
+        assert np.array_equal(np.sort(ids), np.arange(len(pos), dtype=np.uint32))
+        prev_ids = ids
+    sim.close()
+
+
+@pytest.mark.parametrize("name,steps", [("lattice_3d_40k", 40), ("random_30k", 30), ("compressed_6k", 20)])
+def test_multi_step_aggregates(name, steps):
+    """Trajectories diverge chaotically, so after many steps only aggregates are
+    compared: kinetic energy and mean density within 1 %."""
+    pos, vel = STATES[name]()
+    o = CpuOracle(len(pos))
+    o.set_state(pos, vel)
+    sim = make(len(pos))
+    sim.set_state(pos, vel)
+    for _ in range(steps):
+        o.step()
+    sim.advance(steps)
+    ke_o, rho_o = o.stats()
+    ke_g, rho_g = sim.get_stats()
+    assert abs(ke_g - ke_o) <= 0.01 * abs(ke_o) + 1e-9
+    assert abs(rho_g - rho_o) <= 0.01 * rho_o
+    sim.close()
+
+
+def test_graph_and_plain_launch_paths_agree_bitwise():
+    pos, vel = random_state(30000, seed=5, vel_scale=1.0)
+    out = []
+    for use_graph in (True, False):
+        s = sph.Settings(numParticles=len(pos))
+        sim = sph.Simulator(s, use_graph=use_graph)
+        sim.setup()
+        sim.set_state(pos, vel)
+        sim.advance(7)
+        out.append(sim.get_state())
+        sim.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+def test_flat_and_morton_sorts_give_same_physics():
+    pos, vel = compressed_state(5000, seed=3)
+    res = []
+    for mode in (sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON):
+        sim = make(len(pos), key_mode=mode)
+        sim.set_state(pos, vel)
+        sim.simulate()
+        res.append(sim.get_density_pressure_force() + sim.get_state())
+        sim.close()
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-6)
+    np.testing.assert_allclose(res[0][3], res[1][3], rtol=1e-5, atol=1e-6)
+
+
+def test_timed_step_fills_reference_buckets():
+    sim = make(10000)
+    t = sph.Times()
+    for _ in range(5):
+        sim.simulateAndTime(t)
+    assert t.iters == 5 and t.buildGrid > 0 and t.sphUpdate > 0 and t.memcpy > 0
+    sim.close()
+
+
+def test_mouse_push_matches_oracle():
+    pos, vel = random_state(40000, seed=13, lo=3.0, hi=7.0)
+    o = CpuOracle(len(pos))
+    o.set_state(pos, vel)
+    o.step()
+    o.push(pos, 400, 300)          # grid of the PRE-step positions
+    sim = make(len(pos))
+    sim.set_state(pos, vel)
+    sim.simulate()
+    sim.moveParticles((400, 300))
+    p1, v1 = sim.get_state()
+    pushed = np.any(np.abs(o.vel - v1) > 1.0, axis=1)
+    assert not pushed.any(), f"{pushed.sum()} particles pushed differently"
+    assert (np.abs(o.vel[:, 2]) > 4).sum() > 0  # the push actually hit something
+    sim.close()
+
+
+def test_scaled_domain_256_cells():
+    """Config 3 geometry (h=.1, boxDim=25.6, 256 cells) at a test-sized N."""
+    from oracle.oracle import CpuOracle
+    n = 283 * 283 + 1000
+    o = CpuOracle(n, boxDim=25.6, numCellsPerDim=256)
+    o.setup()
+    pos = o.pos.copy()
+    o.step()
+    for mode in (sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON):
+        sim = make(n, key_mode=mode, boxDim=25.6, numCellsPerDim=256.0)
+        cells, ff, fi, mo = o.keys(pos)
+        np.testing.assert_array_equal(sim.get_keys(sph.SPH_KEY_FLAT), fi.astype(np.uint32))
+        sim.simulate()
+        np.testing.assert_array_equal(sim.getPosition(), o.pos)
+        sim.close()
+
+
+@pytest.mark.parametrize("n,init", [(1 << 20, "random"), (4_000_000, "grid")])
+def test_full_size_properties(n, init):
+    """At BASELINE sizes the oracle is too slow; check size-independent properties:
+    sortedness, permutation, cell-table consistency, id-order readback."""
+    box, cells = (10.0, 100.0) if init == "random" else (25.6, 256.0)
+    sim = make(n, randomInit=(init == "random"), boxDim=box, numCellsPerDim=cells)
+    p0, _ = sim.get_state()
+    sim.simulate()
+    ids, skeys = sim.get_sorted_index()
+    assert np.all(np.diff(skeys.astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
+    start = sim.get_cell_start()
+    assert start[0] == 0 and start[-1] == n and np.all(np.diff(start.astype(np.int64)) >= 0)
+    np.testing.assert_array_equal(np.diff(start.astype(np.int64)), np.bincount(skeys, minlength=len(start) - 1))
+    # step 1 is free fall (F == 0): x and z untouched, y moved by g*dt*dt or clamped
+    p1 = sim.getPosition()
+    np.testing.assert_array_equal(p1[:, [0, 2]], p0[:, [0, 2]])
+    dy = np.float32(np.float32(-9.8) * np.float32(0.01)) * np.float32(0.01)
+    np.testing.assert_allclose(p1[:, 1], np.maximum(p0[:, 1] + dy, np.float32(0.1)), atol=2e-6)
+    sim.advance(3)
+    ke, mrho = sim.get_stats()
+    assert np.isfinite(ke) and 25 < mrho < 2000
+    sim.close()
