@@ -41,7 +41,8 @@ class SphOptions(C.Structure):
         ("device", C.c_int32), ("key_mode", C.c_int32), ("record_force", C.c_int32),
         ("use_graph", C.c_int32), ("capacity", C.c_int32),
         ("z_cell_lo", C.c_int32), ("z_cell_hi", C.c_int32),
-        ("reserved", C.c_int32 * 9),
+        ("no_mask_handoff", C.c_int32),
+        ("reserved", C.c_int32 * 8),
     ]
 
 

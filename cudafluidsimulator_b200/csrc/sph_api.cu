@@ -129,7 +129,7 @@ void enqueue_build(sph_sim *s) {
 // "update": the reference's "SPH update" bucket.
 void enqueue_update(sph_sim *s) {
     stage_begin(s, kStDensity);
-    launch_density(s->p, s->d, false, s->stream);
+    launch_density(s->p, s->th, s->d, false, s->stream);
     stage_end(s);
     stage_begin(s, kStForce);
     launch_force_integrate(s->p, s->th, s->d, s->stream);
@@ -213,7 +213,7 @@ int free_device(sph_sim *s) {
     cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
     cudaFree(d.key); cudaFree(d.pairs[0]); cudaFree(d.pairs[1]); cudaFree(d.cell_start);
     cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(d.out_pos);
-    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts);
+    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits);
     memset(&d, 0, sizeof(d));
     if (s->host_pos) cudaFreeHost(s->host_pos);
     s->host_pos = nullptr;
@@ -408,6 +408,10 @@ int sph_setup(sph_sim *s) {
     CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
     if (s->opt.record_force) CU(cudaMalloc(&d.force, cap * sizeof(float4)));
+    if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
+        const size_t ctas = (cap + kBlock - 1) / kBlock;
+        CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));
+    }
     CU(cudaMemset(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
     CU(cudaMemset(d.rho, 0, cap * sizeof(float)));
     CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
@@ -608,7 +612,7 @@ int sph_get_neighbor_counts(sph_sim *s, int32_t *K, int32_t *C) {
     if (!s->d.counts) CU(cudaMalloc(&s->d.counts, sizeof(int32_t) * 2 * (size_t)s->capacity));
     enqueue_build(s);  // grid of the CURRENT positions; the state itself is untouched
     stage_begin(s, kStDensity);
-    launch_density(s->p, s->d, true, s->stream);
+    launch_density(s->p, s->th, s->d, true, s->stream);
     stage_end(s);
     s->step_valid = false;  // rho/pa/force no longer line up with the sorted slots
     std::vector<int32_t> h((size_t)2 * n);

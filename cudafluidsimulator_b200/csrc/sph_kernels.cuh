@@ -21,7 +21,13 @@ struct DeviceState {
     uint32_t *sort_scratch;
     double *stats;               // 2 doubles
     int32_t *counts;             // optional 2*n scratch for K and C
+    uint32_t *nbits;             // in-range bit masks density hands to force (dense particles);
+                                 // kMaskWords words per particle, [CTA][word][lane] interleaved
 };
+
+constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
+constexpr int kMaskWords = 64;   // mask capacity per particle: 64 words = up to 2048 candidates
+constexpr int kDenseMin = 64;    // stencils with more candidates than this use the mask hand-off
 
 // Predicate thresholds on r^2 that are exactly equivalent to the reference's
 // predicates on r = sqrt_rn(r^2) (ref: simulator.cu:110 `dist < EPS_F`,
@@ -33,7 +39,8 @@ struct Thresholds {
 
 void launch_hash(const Params &p, const DeviceState &d, cudaStream_t s);
 void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int sm_count, cudaStream_t s);
-void launch_density(const Params &p, const DeviceState &d, bool counts, cudaStream_t s);
+void launch_density(const Params &p, const Thresholds &t, const DeviceState &d, bool counts,
+                    cudaStream_t s);
 void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);
 void launch_push(const Params &p, const DeviceState &d, int click_x, int click_y, cudaStream_t s);
 void launch_stats(const Params &p, const DeviceState &d, cudaStream_t s);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kSortThreads)
 // is a fully coalesced 256-byte (128-byte for FIRST) request and the order of
 // (item, lane) inside a warp is the array order -- needed for stability.
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
     k_onesweep(const uint32_t *__restrict__ keys_in, const uint64_t *__restrict__ pairs_in,
                uint64_t *__restrict__ pairs_out, int n, int shift,
                const uint32_t *__restrict__ ghist,  // 256 counts of this digit

@@ -83,7 +83,9 @@ typedef struct SphOptions {
     /* slab decomposition (multi-GPU); z_cell_lo == z_cell_hi == 0 => whole box  */
     int32_t z_cell_lo;    /* first owned cell layer along z                      */
     int32_t z_cell_hi;    /* one past the last owned cell layer                  */
-    int32_t reserved[9];
+    int32_t no_mask_handoff; /* 1: force kernel repeats every distance test instead of
+                             reading density's in-range bit masks (A/B measurements)   */
+    int32_t reserved[8];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */

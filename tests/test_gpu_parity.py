@@ -268,3 +268,26 @@ def test_full_size_properties(n, init):
     ke, mrho = sim.get_stats()
     assert np.isfinite(ke) and 25 < mrho < 2000
     sim.close()
+
+
+def test_mask_handoff_is_bitwise_neutral():
+    """Dense particles (C > 64) read density's in-range bit masks in the force kernel;
+    pair order and arithmetic are unchanged, so results must be bit-identical to the
+    path that repeats every distance test."""
+    pos, vel = compressed_state(12000, seed=17)
+    rng = np.random.default_rng(18)   # add a sparse halo so both paths run in one launch
+    halo = rng.uniform(1.0, 9.0, size=(20000, 3)).astype(np.float32)
+    pos = np.concatenate([pos, halo]); vel = np.concatenate([vel, np.zeros_like(halo)])
+    out = []
+    for handoff in (True, False):
+        sim = sph.Simulator(sph.Settings(numParticles=len(pos)), record_force=True, mask_handoff=handoff)
+        sim.setup()
+        sim.set_state(pos, vel)
+        sim.simulate()
+        K, C = None, None
+        rho, prs, f = sim.get_density_pressure_force()
+        sim.advance(4)
+        out.append((rho, f) + sim.get_state())
+        sim.close()
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
