@@ -213,7 +213,7 @@ int free_device(sph_sim *s) {
     cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
     cudaFree(d.key); cudaFree(d.pairs[0]); cudaFree(d.pairs[1]); cudaFree(d.cell_start);
     cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(d.out_pos);
-    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits);
+    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits); cudaFree(d.pair_xy); cudaFree(d.pair_z);
     memset(&d, 0, sizeof(d));
     if (s->host_pos) cudaFreeHost(s->host_pos);
     s->host_pos = nullptr;
@@ -408,6 +408,10 @@ int sph_setup(sph_sim *s) {
     CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
     if (s->opt.record_force) CU(cudaMalloc(&d.force, cap * sizeof(float4)));
+    if (s->p.key_mode == SPH_KEY_FLAT) {
+        CU(cudaMalloc(&d.pair_xy, ((cap + 1) / 2) * sizeof(float4)));
+        CU(cudaMalloc(&d.pair_z, ((cap + 1) / 2) * sizeof(float2)));
+    }
     if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
         const size_t ctas = (cap + kBlock - 1) / kBlock;
         CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));

@@ -11,6 +11,8 @@ namespace sph {
 struct DeviceState {
     float4 *cur_pos, *cur_vel;   // state (input of the step, overwritten with its output)
     float4 *srt_pos, *srt_vel;   // sorted copy of the pre-step state
+    float4 *pair_xy;             // sorted positions again, two slots per record: {x0,x1,y0,y1}
+    float2 *pair_z;              //   and {z0,z1}: operands of the packed f32x2 neighbour loop
     uint32_t *key;               // cell key of cur_pos[i]
     uint64_t *pairs[2];          // (key << 32 | slot) ping-pong buffers of the sort
     uint32_t *cell_start;        // table_size + 1 entries
@@ -21,13 +23,12 @@ struct DeviceState {
     uint32_t *sort_scratch;
     double *stats;               // 2 doubles
     int32_t *counts;             // optional 2*n scratch for K and C
-    uint32_t *nbits;             // in-range bit masks density hands to force (dense particles);
-                                 // kMaskWords words per particle, [CTA][word][lane] interleaved
+    uint32_t *nbits;             // in-range bit masks density hands to force; kMaskWords words
+                                 // per particle, [CTA][word][lane] interleaved
 };
 
 constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
 constexpr int kMaskWords = 64;   // mask capacity per particle: 64 words = up to 2048 candidates
-constexpr int kDenseMin = 64;    // stencils with more candidates than this use the mask hand-off
 
 // Predicate thresholds on r^2 that are exactly equivalent to the reference's
 // predicates on r = sqrt_rn(r^2) (ref: simulator.cu:110 `dist < EPS_F`,
