@@ -31,6 +31,20 @@ __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Lanes of the warp holding the same 8-bit digit: eight ballots intersected.  (The
+// MATCH.ANY instruction computes the same thing but at a small fraction of the ballot
+// rate -- measured: the pass ran at IPC 0.9 with its warps parked on the match results.)
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool set = (d >> bit) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, set);
+        peers &= set ? b : ~b;
+    }
+    return peers;
+}
+
 // Exclusive scan over the 256 threads of a block; `total` = sum of all inputs.
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*8*/,
                                                              uint32_t &total) {
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(kSortThreads)
 // is a fully coalesced 256-byte (128-byte for FIRST) request and the order of
 // (item, lane) inside a warp is the array order -- needed for stability.
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads, 4)
+__global__ void __launch_bounds__(kSortThreads, 3)
     k_onesweep(const uint32_t *__restrict__ keys_in, const uint64_t *__restrict__ pairs_in,
                uint64_t *__restrict__ pairs_out, int n, int shift,
                const uint32_t *__restrict__ ghist,  // 256 counts of this digit
@@ -154,22 +168,39 @@ __global__ void __launch_bounds__(kSortThreads, 4)
     }
 
     // -- stable rank of every item among equal digits of its warp ---------------
+    // A batch of independent peer masks first, then the (serial, shared-memory) counter
+    // updates of that batch.
     uint32_t rank[kSortItems];
+    constexpr int kBatch = 8;
+#if defined(SORT_EXP) && (SORT_EXP & 2)   // microbenchmark only: no ranking (wrong result)
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-        const uint32_t d = (uint32_t)(item[k] >> (32 + shift)) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = s_whist[warp][d];
-            s_whist[warp][d] = old + __popc(peers);
+    for (int k = 0; k < kSortItems; ++k) rank[k] = 0;
+    if (lane == 0) s_whist[warp][item[0] >> (32 + shift) & 255u] = 0;
+#else
+#pragma unroll
+    for (int k0 = 0; k0 < kSortItems; k0 += kBatch) {
+        uint32_t peers[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const uint32_t d = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
+            peers[j] = match_digit(d);
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = old + below;
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const uint32_t d = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
+            const int leader = __ffs(peers[j]) - 1;
+            const uint32_t below = __popc(peers[j] & ((1u << lane) - 1u));
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = s_whist[warp][d];
+                s_whist[warp][d] = old + __popc(peers[j]);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[k0 + j] = old + below;
+            __syncwarp();
+        }
     }
+#endif
     __syncthreads();
 
     // -- per-digit: scan over warps, tile count, look-back -----------------------
@@ -188,15 +219,37 @@ __global__ void __launch_bounds__(kSortThreads, 4)
     const uint32_t dstart = block_exclusive_scan_256(count, s_scan, total);
     const uint32_t gbase = block_exclusive_scan_256(__ldg(ghist + d), s_scan, total);
 
+    // Decoupled look-back, a window of predecessors per step: the status words of
+    // kWindow earlier tiles are fetched together (independent loads), then consumed in
+    // order until an inclusive prefix closes the sum.  A tile whose word is not published
+    // yet is polled again.  (All tiles of a wave start together, so a serial walk would pay
+    // one L2 round trip per running predecessor -- hundreds -- before the first prefix.)
     uint32_t excl = 0;
+#if defined(SORT_EXP) && (SORT_EXP & 1)   // microbenchmark only: no look-back (wrong result)
+    if (false) {
+#else
     if (tile > 0) {
+#endif
+        constexpr int kWindow = 16;
         int prev = (int)tile - 1;
-        while (true) {
-            const uint32_t v = ld_relaxed(status + (size_t)prev * kRadix + d);
-            if ((v & (kFlagAggregate | kFlagInclusive)) == 0) continue;  // not yet published
-            excl += v & kValueMask;
-            if (v & kFlagInclusive) break;
-            --prev;
+        bool closed = false;
+        while (!closed) {
+            uint32_t v[kWindow];
+#pragma unroll
+            for (int j = 0; j < kWindow; ++j)
+                v[j] = (prev - j >= 0) ? ld_relaxed(status + (size_t)(prev - j) * kRadix + d) : kFlagInclusive;
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < kWindow; ++j) {
+                if (!closed && used == j) {
+                    if (v[j] & (kFlagAggregate | kFlagInclusive)) {
+                        excl += v[j] & kValueMask;
+                        closed = (v[j] & kFlagInclusive) != 0;
+                        ++used;
+                    }
+                }
+            }
+            prev -= used;
         }
         st_relaxed(my_status, kFlagInclusive | (excl + count));
     }
@@ -208,7 +261,11 @@ __global__ void __launch_bounds__(kSortThreads, 4)
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
         const uint32_t dd = (uint32_t)(item[k] >> (32 + shift)) & 255u;
+#if defined(SORT_EXP) && (SORT_EXP & 2)
+        s_pairs[tid * kSortItems + k] = item[k];
+#else
         s_pairs[s_dstart[dd] + s_whist[warp][dd] + rank[k]] = item[k];
+#endif
     }
     __syncthreads();
 
@@ -219,7 +276,11 @@ __global__ void __launch_bounds__(kSortThreads, 4)
         if (s < tile_valid) {
             const uint64_t v = s_pairs[s];
             const uint32_t dd = (uint32_t)(v >> (32 + shift)) & 255u;
+#if defined(SORT_EXP) && (SORT_EXP & 4)   // microbenchmark only: linear output (wrong result)
+            pairs_out[base + s] = v + dd + s_goff[dd];
+#else
             pairs_out[s_goff[dd] + (uint32_t)s] = v;
+#endif
         }
     }
 }
