@@ -42,8 +42,23 @@ class SphOptions(C.Structure):
         ("use_graph", C.c_int32), ("capacity", C.c_int32),
         ("z_cell_lo", C.c_int32), ("z_cell_hi", C.c_int32),
         ("no_mask_handoff", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("nz_cells", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
+
+
+class SphSlabInfo(C.Structure):
+    _fields_ = [("n_owned", C.c_int32), ("n_total", C.c_int32), ("slot0", C.c_int32),
+                ("lo_first", C.c_int32), ("lo_count", C.c_int32),
+                ("hi_first", C.c_int32), ("hi_count", C.c_int32),
+                ("emig_count", C.c_int32 * 2), ("overflow", C.c_int32)]
+
+
+class SphSlabBuffers(C.Structure):
+    _fields_ = [("srt_pos", C.c_void_p), ("srt_vel", C.c_void_p), ("pa", C.c_void_p),
+                ("cur_pos", C.c_void_p), ("cur_vel", C.c_void_p),
+                ("emig_pos", C.c_void_p * 2), ("emig_vel", C.c_void_p * 2),
+                ("capacity", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32)]
 
 
 # every symbol include/sph_b200.h declares: name -> (restype, argtypes)
@@ -72,6 +87,14 @@ SYMBOLS = {
     "sph_get_neighbor_counts": (C.c_int, [_P, _I, _I]),
     "sph_get_density_pressure_force": (C.c_int, [_P, _F, _F, _F]),
     "sph_get_stats": (C.c_int, [_P, _D, _D]),
+    "sph_slab_load": (C.c_int, [_P, C.c_int, _F, _F, _U]),
+    "sph_slab_build": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
+    "sph_slab_density": (C.c_int, [_P, C.c_int, C.c_int]),
+    "sph_slab_force": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
+    "sph_slab_append": (C.c_int, [_P, C.c_int]),
+    "sph_slab_buffers": (C.c_int, [_P, C.POINTER(SphSlabBuffers)]),
+    "sph_slab_download": (C.c_int, [_P, _U, _F, _F, _I]),
+    "sph_set_stream": (C.c_int, [_P, C.c_void_p]),
     "sph_profile_enable": (C.c_int, [_P, C.c_int]),
     "sph_profile_read": (C.c_int, [_P, _D, C.POINTER(C.c_int64), C.c_int]),
     "sph_stage_name": (C.c_char_p, [C.c_int]),

@@ -5,6 +5,7 @@
 // whole step replayed as a CUDA graph, one synchronisation per step (the reference
 // synchronises the device three to four times per step and clears its grid with 10^6
 // one-thread blocks).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -64,6 +65,13 @@ struct sph_sim {
     cudaStream_t stream = nullptr;
     float *host_pos = nullptr;  // pinned, 3*n floats, original order
     bool is_setup = false;
+    bool own_stream = true;
+    // slab mode
+    int ghost_cap = 0;          // == p.slot0
+    int n_total = 0;            // entries of the cur arrays in use
+    int n_dead = 0;             // of which emigrated (dropped by the next build)
+    int hashed_upto = 0;        // keys of cur[0, hashed_upto) are valid
+    int slab_overflow = 0;
     bool keys_valid = false;    // d.key matches d.cur_pos
     bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
     cudaGraphExec_t graph = nullptr;
@@ -312,8 +320,27 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
     p.hi = st->boxDim - st->h;
     p.dt = st->timestep;
     p.key_mode = s->opt.key_mode;
+    p.slab = 0; p.slot0 = 0; p.zoff = 0; p.ncz = nc; p.zlo = 0; p.zhi = nc; p.nz = nc;
+    p.hi_z = p.hi; p.dead_key = 0xffffffffu;
+    if (s->opt.z_cell_hi > s->opt.z_cell_lo) {   // slab mode
+        const int nz = s->opt.nz_cells > 0 ? s->opt.nz_cells : nc;
+        if (p.key_mode != SPH_KEY_FLAT || s->opt.z_cell_lo < 0 || s->opt.z_cell_hi > nz) {
+            delete s;
+            return fail(SPH_E_INVALID, "slab mode needs flat keys and 0 <= z_cell_lo < z_cell_hi <= nz_cells");
+        }
+        p.slab = 1;
+        p.zlo = s->opt.z_cell_lo; p.zhi = s->opt.z_cell_hi; p.nz = nz;
+        p.zoff = p.zlo - 1;
+        p.ncz = p.zhi - p.zlo + 2;
+        p.hi_z = (float)nz * st->h - st->h;
+        if ((double)nc * nc * p.ncz >= (double)(1u << 30)) {
+            delete s;
+            return fail(SPH_E_INVALID, "slab too thick: nc^2 * (layers + 2) must stay below 2^30");
+        }
+    }
     if (p.key_mode == SPH_KEY_FLAT) {
-        p.table_size = (uint32_t)nc * nc * nc;
+        p.table_size = (uint32_t)nc * nc * (uint32_t)p.ncz;
+        if (p.slab) p.dead_key = p.table_size - 1u;
     } else {
         int bits = 0;
         while ((1 << bits) < nc) ++bits;
@@ -338,7 +365,7 @@ void sph_destroy(sph_sim *s) {
             cudaEventDestroy(ep.b);
         }
         free_device(s);
-        if (s->stream) cudaStreamDestroy(s->stream);
+        if (s->stream && s->own_stream) cudaStreamDestroy(s->stream);
     }
     delete s;
 }
@@ -348,11 +375,13 @@ int sph_setup(sph_sim *s) {
     if (!s) return fail(SPH_E_INVALID, "null simulator handle");
     if (s->is_setup) return fail(SPH_E_STATE, "sph_setup() called twice");
     const SphSettings &st = s->settings;
-    const int n = s->p.n;
+    const int n = s->p.slab ? 0 : s->p.n;   // slab mode: particles come from sph_slab_load()
 
     // -- initial positions, on the host exactly as the reference computes them --
     std::vector<float> pos((size_t)3 * (n > 0 ? n : 1));
-    if (st.randomInit) {
+    if (s->p.slab) {
+        // nothing: the caller decides which particles this slab owns
+    } else if (st.randomInit) {
         // unseeded glibc rand(): three draws per particle in x, y, z order (ref: 430-437)
         for (int i = 0; i < n; ++i) {
             const float x = rand() / (float)RAND_MAX * (st.boxDim - 2.f) + 1.f;
@@ -394,32 +423,51 @@ int sph_setup(sph_sim *s) {
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     const size_t cap = (size_t)(s->capacity > 0 ? s->capacity : 1);
     DeviceState &d = s->d;
+    size_t scap = cap;   // sorted-slot capacity: owned + ghost room on both sides in slab mode
+    if (s->p.slab) {
+        int g = s->opt.ghost_capacity > 0 ? s->opt.ghost_capacity : (int)(cap / 4) + 1024;
+        g = (g + 1) & ~1;   // slot0 must be even (pair-interleaved copy)
+        s->ghost_cap = g;
+        s->p.slot0 = g;
+        scap = cap + 2 * (size_t)g;
+        d.emig_capacity = s->opt.emig_capacity > 0 ? s->opt.emig_capacity : (int)(cap / 16) + 1024;
+        for (int sd = 0; sd < 2; ++sd) {
+            CU(cudaMalloc(&d.emig_pos[sd], (size_t)d.emig_capacity * sizeof(float4)));
+            CU(cudaMalloc(&d.emig_vel[sd], (size_t)d.emig_capacity * sizeof(float4)));
+        }
+        CU(cudaMalloc(&d.emig_count, 2 * sizeof(uint32_t)));
+        CU(cudaMemset(d.emig_count, 0, 2 * sizeof(uint32_t)));
+    }
     CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
     CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
-    CU(cudaMalloc(&d.srt_pos, cap * sizeof(float4)));
-    CU(cudaMalloc(&d.srt_vel, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_pos, scap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_vel, scap * sizeof(float4)));
     CU(cudaMalloc(&d.key, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&d.pairs[0], cap * sizeof(uint64_t)));
     CU(cudaMalloc(&d.pairs[1], cap * sizeof(uint64_t)));
     CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&d.pa, cap * sizeof(float2)));
-    CU(cudaMalloc(&d.rho, cap * sizeof(float)));
-    CU(cudaMalloc(&d.out_pos, cap * 3 * sizeof(float)));
+    CU(cudaMalloc(&d.pa, scap * sizeof(float2)));
+    CU(cudaMalloc(&d.rho, scap * sizeof(float)));
+    if (!s->p.slab) CU(cudaMalloc(&d.out_pos, cap * 3 * sizeof(float)));
     CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
-    if (s->opt.record_force) CU(cudaMalloc(&d.force, cap * sizeof(float4)));
+    if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
     if (s->p.key_mode == SPH_KEY_FLAT) {
-        CU(cudaMalloc(&d.pair_xy, ((cap + 1) / 2) * sizeof(float4)));
-        CU(cudaMalloc(&d.pair_z, ((cap + 1) / 2) * sizeof(float2)));
+        CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2) * sizeof(float4)));
+        CU(cudaMalloc(&d.pair_z, ((scap + 1) / 2) * sizeof(float2)));
     }
     if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
         const size_t ctas = (cap + kBlock - 1) / kBlock;
         CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));
     }
     CU(cudaMemset(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
-    CU(cudaMemset(d.rho, 0, cap * sizeof(float)));
-    CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
-    memset(s->host_pos, 0, cap * 3 * sizeof(float));
+    CU(cudaMemset(d.rho, 0, scap * sizeof(float)));
+    if (!s->p.slab) {
+        CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
+        memset(s->host_pos, 0, cap * 3 * sizeof(float));
+    } else {
+        s->p.n = 0;
+    }
     s->is_setup = true;
     if (n > 0) {
         int rc = upload_state(s, pos.data(), nullptr);
@@ -428,8 +476,12 @@ int sph_setup(sph_sim *s) {
     return 0;
 }
 
+#define NOT_IN_SLAB_MODE(s) \
+    do { if ((s)->p.slab) return fail(SPH_E_STATE, "not available in slab mode (use the sph_slab_* calls)"); } while (0)
+
 int sph_step(sph_sim *s) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
     int rc = enqueue_step(s);
     if (rc) return rc;
@@ -442,6 +494,7 @@ int sph_step(sph_sim *s) {
 // ref: simulator.cu:499-546 -- same wall-clock buckets, launch + sync inside each
 int sph_step_timed(sph_sim *s, SphTimes *times) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (!times) return fail(SPH_E_INVALID, "null times");
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a) {
@@ -474,6 +527,7 @@ int sph_step_timed(sph_sim *s, SphTimes *times) {
 
 int sph_advance(sph_sim *s, int steps) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (steps < 0) return fail(SPH_E_INVALID, "steps < 0");
     if (s->p.n == 0) return 0;
     for (int k = 0; k < steps; ++k) {
@@ -485,6 +539,7 @@ int sph_advance(sph_sim *s, int steps) {
 
 int sph_advance_timed(sph_sim *s, int steps, float *ms) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (steps < 0 || !ms) return fail(SPH_E_INVALID, "bad argument");
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
@@ -503,6 +558,7 @@ int sph_advance_timed(sph_sim *s, int steps, float *ms) {
 
 int sph_push(sph_sim *s, int x, int y) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
     if (!s->step_valid) return fail(SPH_E_STATE, "sph_push() needs the cell table of a step that just ran");
     stage_begin(s, kStPush);
@@ -515,6 +571,7 @@ const float *sph_positions_host(sph_sim *s) { return s ? s->host_pos : nullptr; 
 
 int sph_readback(sph_sim *s) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
     CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
                        cudaMemcpyDeviceToHost, s->stream));
@@ -523,6 +580,7 @@ int sph_readback(sph_sim *s) {
 
 int sph_set_state(sph_sim *s, const float *pos, const float *vel) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (!pos) return fail(SPH_E_INVALID, "null positions");
     if (s->p.n == 0) return 0;
     return upload_state(s, pos, vel);
@@ -530,6 +588,7 @@ int sph_set_state(sph_sim *s, const float *pos, const float *vel) {
 
 int sph_get_state(sph_sim *s, float *pos, float *vel) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     const int n = s->p.n;
     if (n == 0) return 0;
     std::vector<float4> hp, hv;
@@ -550,6 +609,7 @@ int sph_get_state(sph_sim *s, float *pos, float *vel) {
 
 int sph_get_keys(sph_sim *s, int key_mode, uint32_t *keys) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     if (!keys) return fail(SPH_E_INVALID, "null keys");
     if (key_mode != SPH_KEY_FLAT && key_mode != SPH_KEY_MORTON)
         return fail(SPH_E_INVALID, "unknown key_mode %d", key_mode);
@@ -579,6 +639,7 @@ int sph_get_keys(sph_sim *s, int key_mode, uint32_t *keys) {
 
 int sph_get_sorted_index(sph_sim *s, uint32_t *ids, uint32_t *sorted_keys) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     const int n = s->p.n;
     if (n == 0) return 0;
     if (!s->step_valid) return fail(SPH_E_STATE, "no step has run since the state was set");
@@ -611,6 +672,7 @@ int sph_get_cell_start(sph_sim *s, uint32_t *start, uint32_t *table_size) {
 
 int sph_get_neighbor_counts(sph_sim *s, int32_t *K, int32_t *C) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     const int n = s->p.n;
     if (n == 0) return 0;
     if (!s->d.counts) CU(cudaMalloc(&s->d.counts, sizeof(int32_t) * 2 * (size_t)s->capacity));
@@ -636,6 +698,7 @@ int sph_get_neighbor_counts(sph_sim *s, int32_t *K, int32_t *C) {
 
 int sph_get_density_pressure_force(sph_sim *s, float *rho, float *prs, float *force) {
     REQUIRE_SETUP(s);
+    NOT_IN_SLAB_MODE(s);
     const int n = s->p.n;
     if (n == 0) return 0;
     if (!s->step_valid) return fail(SPH_E_STATE, "no step has run since the state was set");
@@ -676,6 +739,177 @@ int sph_get_stats(sph_sim *s, double *ke, double *mean_rho) {
     }
     if (ke) *ke = h[0];
     if (mean_rho) *mean_rho = s->p.n ? h[1] / s->p.n : 0.0;
+    return 0;
+}
+
+// ---- slab decomposition ---------------------------------------------------------------
+#define REQUIRE_SLAB(s)                                                               \
+    do {                                                                              \
+        REQUIRE_SETUP(s);                                                             \
+        if (!(s)->p.slab) return fail(SPH_E_STATE, "simulator was not created in slab mode"); \
+    } while (0)
+
+int sph_set_stream(sph_sim *s, void *cuda_stream) {
+    REQUIRE_SETUP(s);
+    CU(cudaStreamSynchronize(s->stream));
+    drop_graph(s);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return 0;
+}
+
+int sph_slab_buffers(sph_sim *s, SphSlabBuffers *out) {
+    REQUIRE_SLAB(s);
+    if (!out) return fail(SPH_E_INVALID, "null argument");
+    const DeviceState &d = s->d;
+    out->srt_pos = d.srt_pos; out->srt_vel = d.srt_vel; out->pa = d.pa;
+    out->cur_pos = d.cur_pos; out->cur_vel = d.cur_vel;
+    for (int sd = 0; sd < 2; ++sd) { out->emig_pos[sd] = d.emig_pos[sd]; out->emig_vel[sd] = d.emig_vel[sd]; }
+    out->capacity = s->capacity; out->ghost_capacity = s->ghost_cap; out->emig_capacity = d.emig_capacity;
+    return 0;
+}
+
+int sph_slab_load(sph_sim *s, int n, const float *pos, const float *vel, const uint32_t *ids) {
+    REQUIRE_SLAB(s);
+    if (n < 0 || n > s->capacity) return fail(SPH_E_INVALID, "n = %d exceeds the capacity %d", n, s->capacity);
+    if (n && (!pos || !ids)) return fail(SPH_E_INVALID, "null argument");
+    std::vector<float4> hp((size_t)n), hv((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        float w;
+        memcpy(&w, &ids[i], 4);
+        hp[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], w);
+        hv[i] = vel ? make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.f) : make_float4(0, 0, 0, 0);
+    }
+    if (n) {
+        CU(cudaMemcpyAsync(s->d.cur_pos, hp.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d.cur_vel, hv.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    s->n_total = n; s->n_dead = 0; s->hashed_upto = 0; s->p.n = n; s->step_valid = false;
+    return 0;
+}
+
+int sph_slab_append(sph_sim *s, int count) {
+    REQUIRE_SLAB(s);
+    if (count < 0 || s->n_total + count > s->capacity) {
+        s->slab_overflow |= 1;
+        return fail(SPH_E_INVALID, "appending %d particles to %d exceeds the capacity %d", count, s->n_total, s->capacity);
+    }
+    s->n_total += count;
+    return 0;
+}
+
+int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
+    REQUIRE_SLAB(s);
+    if (!info) return fail(SPH_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
+    Params &p = s->p;
+    const int n_sort = s->n_total;
+    const int n_live = s->n_total - s->n_dead;
+    const uint32_t nn = (uint32_t)p.nc * p.nc;
+    uint32_t b[4] = {0, 0, 0, 0};
+    if (n_sort > 0) {
+        // keys of freshly arrived particles (everything after a load)
+        if (s->hashed_upto < n_sort) {
+            stage_begin(s, kStHash);
+            launch_hash_range(p, s->d, s->hashed_upto, n_sort - s->hashed_upto, s->stream);
+            stage_end(s);
+        }
+        SortHooks hooks{s, sort_before, sort_after};
+        s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], n_sort, s->passes,
+                                         s->d.sort_scratch, s->sm_count, s->stream, &hooks);
+    }
+    p.n = n_live;   // emigrated particles carry dead_key and sit behind the live ones
+    stage_begin(s, kStReorder);
+    launch_reorder(p, s->d, s->sorted_buf, s->sm_count, s->stream);
+    stage_end(s);
+    // slot ranges of the lowest (local layer 1) and highest (local layer ncz-2) owned layers
+    const uint32_t *cs = s->d.cell_start;
+    CU(cudaMemcpyAsync(&b[0], cs + nn, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&b[1], cs + 2 * nn, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&b[2], cs + (size_t)nn * (p.ncz - 2), 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&b[3], cs + (size_t)nn * (p.ncz - 1), 4, cudaMemcpyDeviceToHost, s->stream));
+    int rc = sync_stream(s);
+    if (rc) return rc;
+    s->n_total = n_live; s->n_dead = 0; s->hashed_upto = n_live;
+    info->n_owned = n_live; info->n_total = n_live; info->slot0 = p.slot0;
+    info->lo_first = (int)b[0]; info->lo_count = (int)(b[1] - b[0]);
+    info->hi_first = (int)b[2]; info->hi_count = (int)(b[3] - b[2]);
+    if (info->lo_count > s->ghost_cap || info->hi_count > s->ghost_cap) s->slab_overflow |= 2;
+    info->overflow = s->slab_overflow;
+    return 0;
+}
+
+int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
+    REQUIRE_SLAB(s);
+    if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
+        return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
+    const Params &p = s->p;
+    const uint32_t nn = (uint32_t)p.nc * p.nc;
+    stage_begin(s, kStReorder);
+    launch_ghost_prepare(p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
+    stage_end(s);
+    stage_begin(s, kStReorder);
+    launch_ghost_prepare(p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
+    stage_end(s);
+    if (p.n > 0) {
+        stage_begin(s, kStDensity);
+        launch_density(p, s->th, s->d, false, s->stream);
+        stage_end(s);
+    }
+    s->step_valid = true;
+    return 0;
+}
+
+int sph_slab_force(sph_sim *s, SphSlabInfo *info) {
+    REQUIRE_SLAB(s);
+    if (!info) return fail(SPH_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
+    uint32_t cnt[2] = {0, 0};
+    CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
+    if (s->p.n > 0) {
+        stage_begin(s, kStForce);
+        launch_force_integrate(s->p, s->th, s->d, s->stream);
+        stage_end(s);
+    }
+    CU(cudaMemcpyAsync(cnt, s->d.emig_count, sizeof(cnt), cudaMemcpyDeviceToHost, s->stream));
+    int rc = sync_stream(s);
+    if (rc) return rc;
+    for (int sd = 0; sd < 2; ++sd) {
+        if ((int)cnt[sd] > s->d.emig_capacity) s->slab_overflow |= 4;
+        info->emig_count[sd] = (int)std::min<uint32_t>(cnt[sd], (uint32_t)s->d.emig_capacity);
+    }
+    s->n_dead = (int)(cnt[0] + cnt[1]);
+    info->n_owned = s->p.n - s->n_dead; info->n_total = s->n_total; info->slot0 = s->p.slot0;
+    info->overflow = s->slab_overflow;
+    return 0;
+}
+
+int sph_slab_download(sph_sim *s, uint32_t *ids, float *pos, float *vel, int *n_out) {
+    REQUIRE_SLAB(s);
+    const int n = s->n_total;
+    std::vector<float4> hp((size_t)n), hv((size_t)n);
+    std::vector<uint32_t> hk((size_t)n);
+    if (n) {
+        if (s->hashed_upto < n) {   // keys are needed to tell dead entries apart
+            launch_hash_range(s->p, s->d, s->hashed_upto, n - s->hashed_upto, s->stream);
+            s->hashed_upto = n;
+        }
+        CU(cudaMemcpyAsync(hp.data(), s->d.cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(hv.data(), s->d.cur_vel, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(hk.data(), s->d.key, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        if (s->n_dead > 0 && hk[i] == s->p.dead_key) continue;
+        if (ids) ids[m] = id_of(hp[i]);
+        if (pos) { pos[3 * m] = hp[i].x; pos[3 * m + 1] = hp[i].y; pos[3 * m + 2] = hp[i].z; }
+        if (vel) { vel[3 * m] = hv[i].x; vel[3 * m + 1] = hv[i].y; vel[3 * m + 2] = hv[i].z; }
+        ++m;
+    }
+    if (n_out) *n_out = m;
     return 0;
 }
 

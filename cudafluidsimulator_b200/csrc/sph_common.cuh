@@ -32,7 +32,17 @@ struct Params {
     float hi;       // boxDim - h, rounded once (ref: simulator.cu:283)
     float dt;       // timestep
     int key_mode;   // KeyMode
-    uint32_t table_size;  // number of distinct keys (nc^3 flat, 8^bits Morton)
+    uint32_t table_size;  // number of distinct keys (nc^2 * ncz flat, 8^bits Morton)
+    // -- slab decomposition along z (multi-GPU); single GPU: slot0 = 0, zoff = 0, ncz = nc,
+    //    [zlo, zhi) = [0, nc), nz = nc, hi_z = hi
+    int slab;       // 1 in slab mode
+    int slot0;      // first target slot of the sorted arrays (ghost capacity in slab mode)
+    int zoff;       // global z cell of local layer 0 (slab: zlo - 1, the low ghost layer)
+    int ncz;        // local layers along z (slab: owned + 2 ghost layers)
+    int zlo, zhi;   // owned global z-cell layers [zlo, zhi)
+    int nz;         // global cells along z
+    float hi_z;     // global box length along z minus h (z wall)
+    uint32_t dead_key;  // slab: key given to emigrated particles; sorts behind every live key
 };
 
 // ---- cell coordinates and keys ------------------------------------------------
@@ -42,6 +52,14 @@ struct Params {
 __device__ __forceinline__ int cell_coord(float x, const Params &p) {
     int c = __float2int_rz(__fdiv_rn(x, p.h));
     return min(max(c, 0), p.nc - 1);
+}
+// z: the GLOBAL cell (same IEEE rule), and the layer index local to this slab
+__device__ __forceinline__ int cell_coord_zglobal(float z, const Params &p) {
+    int c = __float2int_rz(__fdiv_rn(z, p.h));
+    return min(max(c, 0), p.nz - 1);
+}
+__device__ __forceinline__ int cell_coord_z(float z, const Params &p) {
+    return min(max(cell_coord_zglobal(z, p) - p.zoff, 0), p.ncz - 1);
 }
 
 __device__ __forceinline__ uint32_t spread3(uint32_t v) {
@@ -87,7 +105,7 @@ __device__ __forceinline__ void for_each_run(const Params &p, int cx, int cy, in
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
         const int zz = cz + dz;
-        if (zz < 0 || zz >= p.nc) continue;
+        if (zz < 0 || zz >= p.ncz) continue;
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
             const int yy = cy + dy;

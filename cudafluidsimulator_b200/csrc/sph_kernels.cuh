@@ -25,6 +25,10 @@ struct DeviceState {
     int32_t *counts;             // optional 2*n scratch for K and C
     uint32_t *nbits;             // in-range bit masks density hands to force; kMaskWords words
                                  // per particle, [CTA][word][lane] interleaved
+    // slab mode: particles that left the owned z-layers during integration, per side
+    float4 *emig_pos[2], *emig_vel[2];   // [0] towards lower z, [1] towards higher z
+    uint32_t *emig_count;                // 2 counters (may exceed emig_capacity: overflow)
+    int emig_capacity;
 };
 
 constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
@@ -45,5 +49,11 @@ void launch_density(const Params &p, const Thresholds &t, const DeviceState &d, 
 void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);
 void launch_push(const Params &p, const DeviceState &d, int click_x, int click_y, cudaStream_t s);
 void launch_stats(const Params &p, const DeviceState &d, cudaStream_t s);
+// slab mode: hash of freshly appended particles [first, first+count) of the cur arrays
+void launch_hash_range(const Params &p, const DeviceState &d, int first, int count, cudaStream_t s);
+// slab mode: cell ranges + pair-interleaved copy of the ghost slots [first, first+count) whose
+// keys lie in [key_lo, key_hi); cell_start[k] for k in [key_lo, key_hi] is written
+void launch_ghost_prepare(const Params &p, const DeviceState &d, int first, int count,
+                          uint32_t key_lo, uint32_t key_hi, cudaStream_t s);
 
 }  // namespace sph

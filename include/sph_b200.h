@@ -85,7 +85,11 @@ typedef struct SphOptions {
     int32_t z_cell_hi;    /* one past the last owned cell layer                  */
     int32_t no_mask_handoff; /* 1: force kernel repeats every distance test instead of
                              reading density's in-range bit masks (A/B measurements)   */
-    int32_t reserved[8];
+    int32_t nz_cells;     /* slab mode: global cell layers along z (0 = numCellsPerDim); the
+                             global box is boxDim x boxDim x nz_cells*h                  */
+    int32_t ghost_capacity; /* slab mode: max ghost particles per side (0 = capacity/4)     */
+    int32_t emig_capacity;  /* slab mode: max emigrants per side and step (0 = capacity/16) */
+    int32_t reserved[5];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */
@@ -140,6 +144,57 @@ int sph_get_neighbor_counts(sph_sim *sim, int32_t *K, int32_t *C);
 int sph_get_density_pressure_force(sph_sim *sim, float *rho, float *prs, float *force);
 /* kinetic energy 0.5*m*|v|^2 summed, and mean density of the last step */
 int sph_get_stats(sph_sim *sim, double *kinetic_energy, double *mean_density);
+
+/* --- slab decomposition (multi-GPU; north_star: spatial slabs, per-step ghost halo
+ * exchange and particle migration) ---------------------------------------------------
+ * One simulator per GPU owns the global cell layers [z_cell_lo, z_cell_hi) along z
+ * (SphOptions) and the particles in them.  The library does the compute and exposes the
+ * device buffers; the caller moves halo / migrant ranges between ranks (NCCL send/recv
+ * or P2P copies straight between these buffers, see cudafluidsimulator_b200/slab.py):
+ *
+ *   sph_slab_build    hash (new arrivals) + sort + reorder -> sorted owned particles at
+ *                     slots [slot0, slot0+n_owned) of srt_pos/srt_vel; reports the slot
+ *                     ranges of the lowest / highest owned layer (= what the neighbours
+ *                     need as ghosts)
+ *   [exchange A]      neighbours' boundary layers -> srt_pos/srt_vel ghost slots:
+ *                     low ghosts end at slot0, high ghosts start at slot0+n_owned
+ *   sph_slab_density  cell ranges of the ghosts, density + pressure of owned particles
+ *   [exchange B]      pa of the boundary layers -> pa at the same ghost slots
+ *   sph_slab_force    force + integrate owned particles; particles leaving the slab are
+ *                     packed into emig_pos/emig_vel[side] and dropped at the next build
+ *   [migration]       emigrants -> neighbour's cur_pos/cur_vel at index n_total onwards,
+ *                     then sph_slab_append(count)
+ * There is no reference equivalent (the reference is single-GPU). */
+typedef struct SphSlabInfo {
+    int32_t n_owned;      /* live owned particles                                   */
+    int32_t n_total;      /* entries of cur_pos/cur_vel in use (owned + appended)   */
+    int32_t slot0;        /* first owned sorted slot (= ghost capacity)             */
+    int32_t lo_first, lo_count; /* sorted slots of the lowest owned layer          */
+    int32_t hi_first, hi_count; /* sorted slots of the highest owned layer         */
+    int32_t emig_count[2];      /* emigrants of the last sph_slab_force (down, up) */
+    int32_t overflow;     /* non-zero: a capacity was exceeded, particles were lost */
+} SphSlabInfo;
+
+typedef struct SphSlabBuffers {   /* device pointers, valid until sph_destroy */
+    void *srt_pos, *srt_vel;      /* float4 per sorted slot                  */
+    void *pa;                     /* float2 per sorted slot                  */
+    void *cur_pos, *cur_vel;      /* float4 per particle, storage order      */
+    void *emig_pos[2], *emig_vel[2]; /* float4 per emigrant, per side        */
+    int32_t capacity, ghost_capacity, emig_capacity;
+} SphSlabBuffers;
+
+/* Replace the owned particle set (host arrays; ids are global particle ids). */
+int sph_slab_load(sph_sim *sim, int n, const float *pos, const float *vel, const uint32_t *ids);
+int sph_slab_build(sph_sim *sim, SphSlabInfo *info);
+int sph_slab_density(sph_sim *sim, int ghost_lo_count, int ghost_hi_count);
+int sph_slab_force(sph_sim *sim, SphSlabInfo *info);
+int sph_slab_append(sph_sim *sim, int count);
+int sph_slab_buffers(sph_sim *sim, SphSlabBuffers *out);
+/* Owned live particles (after sph_slab_force: the integrated state), any order. */
+int sph_slab_download(sph_sim *sim, uint32_t *ids, float *pos, float *vel, int *n);
+/* Run every launch of this simulator on the caller's CUDA stream (e.g. torch's current
+ * stream, so that NCCL transfers and kernels are ordered without extra events). */
+int sph_set_stream(sph_sim *sim, void *cuda_stream);
 
 /* --- measurement -------------------------------------------------------------
  * Per-kernel CUDA-event times (ms, summed since the last reset) for the stages

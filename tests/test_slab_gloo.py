@@ -1,0 +1,82 @@
+"""CPU suite, world_size 2 over gloo: the slab driver's halo-exchange / migration
+protocol (cudafluidsimulator_b200/slab.py) with a CPU stand-in for the library, compared
+with the undecomposed CPU oracle.  The GPU kernels of slab mode are covered by
+tests/test_gpu_slab.py on a multi-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import random_state
+from cudafluidsimulator_b200.slab import SlabDriver, partition, slab_ranges
+
+
+def test_slab_ranges_cover_and_balance():
+    for nz, w in [(100, 1), (100, 3), (256, 8), (7, 8)]:
+        r = slab_ranges(nz, w)
+        assert r[0][0] == 0 and r[-1][1] == nz and len(r) == w
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_partition_uses_reference_cell_rule():
+    pos = np.float32([[5, 5, 0.1], [5, 5, 4.9999], [5, 5, 5.0], [5, 5, 9.9]])
+    parts = partition(pos, 0.1, [(0, 50), (50, 100)])
+    assert parts[0].tolist() == [0, 1] and parts[1].tolist() == [2, 3]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, pos, vel, steps, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from fake_slab import FakeSlab
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ranges = slab_ranges(100, world)
+    mine = partition(pos, 0.1, ranges)[rank]
+    b = FakeSlab(*ranges[rank], 100, capacity=len(pos), ghost_capacity=len(pos), emig_capacity=len(pos))
+    b.load(pos[mine], vel[mine], mine.astype(np.uint32))
+    drv = SlabDriver(b, rank, world)
+    for _ in range(steps):
+        drv.step()
+    ids, p, v = b.download()
+    out[rank] = (ids, p, v, drv.stats)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_slabs_match_undecomposed_oracle(world):
+    from oracle.oracle import CpuOracle
+    # a blob straddling the slab boundary at z = 5.0 (and 3.4 / 6.7 for three slabs), moving in z
+    rng = np.random.default_rng(5)
+    n = 3000
+    pos = (np.float32([3.0, 3.0, 3.0]) + rng.uniform(0, 1.0, (n, 3)) * np.float32([0.6, 0.6, 4.0])).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * np.float32([0.5, 0.5, 6.0])).astype(np.float32)
+    steps = 6
+    o = CpuOracle(n)
+    o.set_state(pos, vel)
+    for _ in range(steps):
+        o.step()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), pos, vel, steps, out), nprocs=world, join=True)
+    ids = np.concatenate([out[r][0] for r in range(world)])
+    p = np.concatenate([out[r][1] for r in range(world)])
+    v = np.concatenate([out[r][2] for r in range(world)])
+    assert sorted(ids.tolist()) == list(range(n)), "particles lost or duplicated by migration"
+    order = np.argsort(ids)
+    np.testing.assert_allclose(p[order], o.pos, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(v[order], o.vel, rtol=1e-3, atol=1e-3)
+    assert sum(out[r][3]["migrated_particles"] for r in range(world)) > 0   # migration exercised
+    assert sum(out[r][3]["ghost_particles"] for r in range(world)) > 0     # halos exercised
