@@ -193,7 +193,154 @@ def flops_per_particle(C, K):
     return (9 * C + 6 * K + 3), (9 * C + 32 * K), 30.0
 
 
+def lattice_positions(n, h, box, z_shift=0.0):
+    """The reference's grid init (ref: simulator.cu:438-453) vectorised: float32 multiply and
+    add, separately rounded, x outer / z inner; optional shift along z for replicated sub-boxes."""
+    h32, sp = np.float32(h), np.float32(0.9) * np.float32(h)
+    nx = int(np.floor((np.float32(box) - np.float32(2) * h32) / sp) + 1)
+    i = np.arange(n, dtype=np.int64)
+    ix, iy, iz = i // (nx * nx), (i // nx) % nx, i % nx
+    pos = np.empty((n, 3), np.float32)
+    pos[:, 0] = h32 + sp * ix.astype(np.float32)
+    pos[:, 1] = h32 + sp * iy.astype(np.float32)
+    pos[:, 2] = h32 + sp * iz.astype(np.float32)
+    if z_shift:
+        pos[:, 2] += np.float32(z_shift)
+    return pos
+
+
+def run_slabs(args, wl, rank, local_rank, world):
+    """N > 1: weak scaling, one slab per GPU.  The N=1 workload (sub-box) is replicated along
+    z (the decomposition axis); the interfaces between sub-boxes are open, so every step does a
+    real ghost halo exchange (pos/vel, then pressure terms) and particle migration over NCCL."""
+    import torch
+    import torch.distributed as dist
+    import cudafluidsimulator_b200 as sph
+    from cudafluidsimulator_b200.slab import SlabBackend, SlabDriver
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cudafluidsimulator_b200.slab import partition, slab_ranges
+    nc = int(wl["numCellsPerDim"])
+    h32, box = np.float32(0.1), wl["boxDim"]
+    st = sph.Settings(numParticles=wl["n"], randomInit=wl["randomInit"], boxDim=box,
+                      numCellsPerDim=wl["numCellsPerDim"])
+    # Global problem = the N=1 workload stretched `world` times along z:
+    #   grid  : the reference lattice (0.9h spacing from (h,h,h), x outer / z inner) with the same
+    #           number of x-planes as the N=1 case and world x as many lattice points along z --
+    #           one continuous fluid column across all slabs (real halos, real migration)
+    #   random: uniform in the stretched box interior
+    if wl["randomInit"]:
+        nz = nc * world
+        ranges = slab_ranges(nz, world)
+        rng = np.random.default_rng(1234)
+        n_glob = wl["n"] * world
+        # every rank draws the same global set and keeps its slab (cheap at 1M x world)
+        gpos = rng.uniform(1.0, box - 1.0, (n_glob, 3)).astype(np.float32)
+        gpos[:, 2] = (np.float32(1.0) + rng.uniform(0, 1, n_glob).astype(np.float32) * np.float32(box * world - 2.0))
+        mine = partition(gpos, 0.1, ranges)[rank]
+        my_pos, my_ids = gpos[mine], mine.astype(np.uint32)
+    else:
+        sp = np.float32(0.9) * h32
+        nl = int(np.floor((np.float32(box) - np.float32(2) * h32) / sp) + 1)     # 283 lattice points per box edge
+        planes = int(np.ceil(wl["n"] / (nl * nl)))                                # x-planes of the N=1 case
+        # two lattice points fewer per slab than the N=1 box: keeps (owned + 2 ghost) layers x nc^2
+        # below 2^24 keys, i.e. the same three 8-bit sort passes as on one GPU
+        nlz = (nl - 2) * world
+        zs = h32 + sp * np.arange(nlz, dtype=np.float32)
+        nz = int(np.floor(zs[-1] / h32)) + 2                                       # + wall layer
+        ranges = slab_ranges(nz, world)
+        cz = (zs / h32).astype(np.int64)
+        iz = np.nonzero((cz >= ranges[rank][0]) & (cz < ranges[rank][1]))[0]
+        ix, iy, izz = np.meshgrid(np.arange(planes), np.arange(nl), iz, indexing="ij")
+        my_pos = np.empty((ix.size, 3), np.float32)
+        my_pos[:, 0] = (h32 + sp * ix.astype(np.float32)).ravel()
+        my_pos[:, 1] = (h32 + sp * iy.astype(np.float32)).ravel()
+        my_pos[:, 2] = zs[izz.ravel()]
+        my_ids = ((ix.ravel().astype(np.int64) * nl + iy.ravel()) * nlz + izz.ravel()).astype(np.uint32)
+        n_glob = planes * nl * nlz
+    n = len(my_ids)
+    zlo, zhi = ranges[rank]
+
+    def make():
+        b = SlabBackend(st, zlo, zhi, nz, capacity=int(n * 1.2) + 4096, device=local_rank,
+                        ghost_capacity=int(n * 0.1) + 4096, emig_capacity=int(n * 0.05) + 4096)
+        b.load(my_pos, np.zeros_like(my_pos), my_ids)
+        return b, SlabDriver(b, rank, world)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -- device-resident timed region ---------------------------------------------------
+    b, drv = make()
+    for _ in range(args.warmup):
+        drv.step()
+    l0 = b.launch_count
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(drv.step, args.steps)
+    launches = b.launch_count - l0
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"rank": rank, **drv.last, **{k: v for k, v in drv.stats.items()}})
+    b.close()
+
+    # -- e2e: every step also copies the owned particles' positions to pinned host memory --
+    b, drv = make()
+    host = torch.empty((b.capacity, 4), dtype=torch.float32).pin_memory()
+    def step_e2e():
+        drv.step()
+        k = drv.last["n_owned"]
+        host[:k].copy_(b.cur_pos[:k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(args.warmup):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    b.close()
+
+    if rank == 0:
+        owned = [r["n_owned"] for r in per_rank]
+        line = {
+            "metric": "particle-updates/s", "value": n_glob * args.steps / (ms * 1e-3),
+            "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n_per_gpu": n_glob // world, "n_total": n_glob, "boxDim": wl["boxDim"],
+                       "numCellsPerDim": wl["numCellsPerDim"], "global_cells_z": nz,
+                       "parallelism": f"{world} z-slabs, one per GPU: ghost halo exchange (pos/vel, then pressure "
+                                      "terms) + particle migration per step over NCCL send/recv",
+                       "init": "N=1 workload stretched along z: one continuous fluid body across all slabs",
+                       "l2": f"state evolves step to step; working set {n * 124 / 1e6:.0f} MB per GPU vs 126 MB L2"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": n_glob * args.steps / (e2e_ms * 1e-3), "unit": "particle-updates/s",
+                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": n_glob * 16,
+                    "api": "SlabDriver.step() + per-step D2H of every owned particle's position record into pinned host memory"},
+            "gpu_launches": int(launches) * world,
+            "load_balance": {"owned_per_rank": owned, "imbalance_max_over_mean": max(owned) / (sum(owned) / world),
+                             "ghosts_last_step": [r["ghosts"] for r in per_rank],
+                             "migrated_total": [r["migrated_particles"] for r in per_rank]},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_ours(args, wl, rank, local_rank, world):
+    if world > 1:
+        return run_slabs(args, wl, rank, local_rank, world)
+
     import torch
     import cudafluidsimulator_b200 as sph
 
