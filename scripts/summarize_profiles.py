@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Turns the ncu artefacts a gpurun call brought back (gpurun_out/) into the committed
+summaries under profiles/:   python scripts/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep>"""
+import collections
+import csv
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+tag, launches, rep = sys.argv[1], Path(sys.argv[2]), Path(sys.argv[3])
+out = ROOT / "profiles"
+out.mkdir(exist_ok=True)
+
+# -- launch list (gpu__time_duration.sum, cold-cache and serialised: compare SHARES) ------
+rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+hdr, data = rows[0], rows[1:]
+ix = {h: i for i, h in enumerate(hdr)}
+agg = collections.OrderedDict()
+with open(out / f"{tag}_launches.csv", "w") as f:
+    f.write("id,kernel,grid,block,duration_ns\n")
+    for r in data:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "")
+        ns = float(r[ix["Metric Value"]].replace(",", ""))
+        f.write(f'{r[ix["ID"]]},{name},{r[ix["Grid Size"]].replace(",", " ")},{r[ix["Block Size"]].replace(",", " ")},{ns:.0f}\n')
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ns / 1e6
+tot = sum(a[1] for a in agg.values())
+lines = [f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu` (16M grid, one B200)",
+         "# ncu --metrics gpu__time_duration.sum --clock-control none; per-launch times are cold-cache and",
+         "# serialised, so only the SHARE of the step is comparable with bench.py's CUDA-event stage times.",
+         "", "| kernel | launches | total ms | share | avg ms |", "|---|---|---|---|---|"]
+for k, (c, t) in agg.items():
+    lines.append(f"| {k} | {c} | {t:.3f} | {100 * t / tot:.1f} % | {t / c:.4f} |")
+
+# -- full capture: one plainly launched step at the developed state ----------------------
+raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+h2, units, d2 = rr[0], rr[1], rr[2:]
+jx = {h: i for i, h in enumerate(h2)}
+want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs/thread"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+        ("sm__inst_executed.avg.per_cycle_active", "IPC (max ~3.6 measured, 4 nominal)"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+        ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instr"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput %"),
+        ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+        ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"),
+        ("smsp__inst_executed.sum", "warp instructions")]
+names = [r[jx["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "") for r in d2]
+lines += ["", f"# {tag}: ncu --set full --clock-control none, ONE plainly launched step of the 16M grid workload at the",
+          "# state after 100 steps (scripts/profile_step.py --pre 100): mean candidates 116, mean neighbours 25.",
+          "", "| metric | " + " | ".join(names) + " |", "|---|" + "---|" * len(names)]
+for key, label in want:
+    if key in jx:
+        vals = []
+        for r in d2:
+            v = r[jx[key]]
+            try:
+                v = f"{float(v.replace(',', '')):.4g}"
+            except ValueError:
+                pass
+            vals.append(f"{v} {units[jx[key]]}".strip())
+        lines.append(f"| {label} | " + " | ".join(vals) + " |")
+stalls = [h for h in h2 if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+lines += ["", "Warp stall reasons (warps stalled per issue; > 0.5 only):", "", "| reason | " + " | ".join(names) + " |",
+          "|---|" + "---|" * len(names)]
+for hname in stalls:
+    vals = [float(r[jx[hname]] or 0) for r in d2]
+    if max(vals) > 0.5:
+        short = hname.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")
+        lines.append(f"| {short} | " + " | ".join(f"{v:.2f}" for v in vals) + " |")
+(out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
+print("\n".join(lines))
