@@ -74,7 +74,13 @@ struct sph_sim {
     int slab_overflow = 0;
     bool keys_valid = false;    // d.key matches d.cur_pos
     bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr;       // step graph writing out_buf[0]
+    cudaGraphExec_t graph_alt = nullptr;   // same step writing out_buf[1] (pipelined readback)
+    float *out_buf[2] = {nullptr, nullptr};
+    int out_parity = 0;
+    bool spec_inflight = false;            // a step is enqueued whose positions were not handed out yet
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
     bool profiling = false;
     std::vector<EventPair> events;
     size_t events_used = 0;
@@ -150,7 +156,8 @@ int graph_launches_per_step(const sph_sim *s) { return 1 /*hist*/ + s->passes + 
 int enqueue_step(sph_sim *s) {
     const bool want_graph = s->opt.use_graph != 2 && !s->profiling;
     if (want_graph && s->keys_valid) {
-        if (!s->graph) {
+        cudaGraphExec_t &graph_slot = s->out_parity ? s->graph_alt : s->graph;
+        if (!graph_slot) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = s->launches;
             int64_t sl0[SPH_STAGE_COUNT];
@@ -161,10 +168,10 @@ int enqueue_step(sph_sim *s) {
             CU(cudaStreamEndCapture(s->stream, &g));
             s->launches = l0;  // capture launches nothing
             memcpy(s->stage_launches, sl0, sizeof(sl0));
-            CU(cudaGraphInstantiate(&s->graph, g, 0));
+            CU(cudaGraphInstantiate(&graph_slot, g, 0));
             cudaGraphDestroy(g);
         }
-        CU(cudaGraphLaunch(s->graph, s->stream));
+        CU(cudaGraphLaunch(graph_slot, s->stream));
         s->launches += graph_launches_per_step(s);
         s->stage_launches[kStHist] += 1;
         s->stage_launches[kStSort] += s->passes;
@@ -187,10 +194,9 @@ int sync_stream(sph_sim *s) {
 }
 
 void drop_graph(sph_sim *s) {
-    if (s->graph) {
-        cudaGraphExecDestroy(s->graph);
-        s->graph = nullptr;
-    }
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    if (s->graph_alt) cudaGraphExecDestroy(s->graph_alt);
+    s->graph = s->graph_alt = nullptr;
 }
 
 float bisect_sqrt_threshold(float target, bool smallest_ge) {
@@ -220,7 +226,10 @@ int free_device(sph_sim *s) {
     DeviceState &d = s->d;
     cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
     cudaFree(d.key); cudaFree(d.pairs[0]); cudaFree(d.pairs[1]); cudaFree(d.cell_start);
-    cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(d.out_pos);
+    cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(s->out_buf[0]); cudaFree(s->out_buf[1]);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->ev_step) cudaEventDestroy(s->ev_step);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits); cudaFree(d.pair_xy); cudaFree(d.pair_z);
     memset(&d, 0, sizeof(d));
     if (s->host_pos) cudaFreeHost(s->host_pos);
@@ -250,6 +259,7 @@ int upload_state(sph_sim *s, const float *pos, const float *vel) {
     CU(cudaStreamSynchronize(s->stream));
     s->keys_valid = false;
     s->step_valid = false;
+    s->spec_inflight = false;
     return 0;
 }
 
@@ -448,7 +458,16 @@ int sph_setup(sph_sim *s) {
     CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.pa, scap * sizeof(float2)));
     CU(cudaMalloc(&d.rho, scap * sizeof(float)));
-    if (!s->p.slab) CU(cudaMalloc(&d.out_pos, cap * 3 * sizeof(float)));
+    if (!s->p.slab) {
+        CU(cudaMalloc(&s->out_buf[0], cap * 3 * sizeof(float)));
+        d.out_pos = s->out_buf[0];
+        if (s->opt.pipeline_readback) {
+            CU(cudaMalloc(&s->out_buf[1], cap * 3 * sizeof(float)));
+            CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
+        }
+    }
     CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
     if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
@@ -479,10 +498,36 @@ int sph_setup(sph_sim *s) {
 #define NOT_IN_SLAB_MODE(s) \
     do { if ((s)->p.slab) return fail(SPH_E_STATE, "not available in slab mode (use the sph_slab_* calls)"); } while (0)
 
+// sph_step() with SphOptions.pipeline_readback: the copy of step k's positions (copy stream)
+// overlaps the computation of step k+1 (compute stream), which is started before returning.
+static int step_pipelined(sph_sim *s) {
+    const size_t bytes = sizeof(float) * 3 * (size_t)s->p.n;
+    int rc = 0;
+    if (!s->spec_inflight) {   // first call, or the state was replaced: compute the step asked for
+        s->d.out_pos = s->out_buf[s->out_parity];
+        rc = enqueue_step(s);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(s->ev_step, s->stream));
+    CU(cudaStreamWaitEvent(s->copy_stream, s->ev_step, 0));
+    CU(cudaMemcpyAsync(s->host_pos, s->out_buf[s->out_parity], bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(s->ev_copy, s->copy_stream));
+    // speculative next step into the other output buffer
+    s->out_parity ^= 1;
+    s->d.out_pos = s->out_buf[s->out_parity];
+    rc = enqueue_step(s);
+    if (rc) return rc;
+    s->spec_inflight = true;
+    CU(cudaEventSynchronize(s->ev_copy));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int sph_step(sph_sim *s) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
+    if (s->opt.pipeline_readback) return step_pipelined(s);
     int rc = enqueue_step(s);
     if (rc) return rc;
     // ref: simulator.cu:478-480 -- blocking copy of every position to the host
@@ -495,6 +540,7 @@ int sph_step(sph_sim *s) {
 int sph_step_timed(sph_sim *s, SphTimes *times) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
+    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (!times) return fail(SPH_E_INVALID, "null times");
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a) {
@@ -528,6 +574,7 @@ int sph_step_timed(sph_sim *s, SphTimes *times) {
 int sph_advance(sph_sim *s, int steps) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
+    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (steps < 0) return fail(SPH_E_INVALID, "steps < 0");
     if (s->p.n == 0) return 0;
     for (int k = 0; k < steps; ++k) {
@@ -540,6 +587,7 @@ int sph_advance(sph_sim *s, int steps) {
 int sph_advance_timed(sph_sim *s, int steps, float *ms) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
+    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (steps < 0 || !ms) return fail(SPH_E_INVALID, "bad argument");
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
@@ -573,6 +621,7 @@ int sph_readback(sph_sim *s) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
+    s->spec_inflight = false;   // the host buffer now shows the internal (latest) step
     CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
                        cudaMemcpyDeviceToHost, s->stream));
     return sync_stream(s);

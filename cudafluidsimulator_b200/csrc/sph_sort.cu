@@ -14,6 +14,20 @@
 // is implicit).
 #include "sph_sort.cuh"
 
+// Tunables of the onesweep pass (see profiles/r01_sort_phase_elimination.txt): resident CTAs
+// per SM and status words fetched per look-back step.  The look-back walk covers every
+// running predecessor tile; it stays short only while
+//   (resident tiles / tile time) x (latency of one step) / window  <<  1.
+#ifndef SORT_CTAS_PER_SM
+#define SORT_CTAS_PER_SM 3
+#endif
+#ifndef SORT_LOOKBACK_WINDOW
+#define SORT_LOOKBACK_WINDOW 16
+#endif
+#ifndef SORT_SPIN_SLEEP_NS
+#define SORT_SPIN_SLEEP_NS 0
+#endif
+
 namespace sph {
 
 namespace {
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(kSortThreads)
 // is a fully coalesced 256-byte (128-byte for FIRST) request and the order of
 // (item, lane) inside a warp is the array order -- needed for stability.
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     k_onesweep(const uint32_t *__restrict__ keys_in, const uint64_t *__restrict__ pairs_in,
                uint64_t *__restrict__ pairs_out, int n, int shift,
                const uint32_t *__restrict__ ghist,  // 256 counts of this digit
@@ -230,7 +244,7 @@ __global__ void __launch_bounds__(kSortThreads, 3)
 #else
     if (tile > 0) {
 #endif
-        constexpr int kWindow = 16;
+        constexpr int kWindow = SORT_LOOKBACK_WINDOW;
         int prev = (int)tile - 1;
         bool closed = false;
         while (!closed) {
@@ -250,6 +264,11 @@ __global__ void __launch_bounds__(kSortThreads, 3)
                 }
             }
             prev -= used;
+#if SORT_SPIN_SLEEP_NS > 0
+            // Blocked on a tile that has not published yet: back off instead of hammering the
+            // issue slots the publishing CTAs on this SM need.
+            if (!closed && used == 0) __nanosleep(SORT_SPIN_SLEEP_NS);
+#endif
         }
         st_relaxed(my_status, kFlagInclusive | (excl + count));
     }

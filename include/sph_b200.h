@@ -89,7 +89,13 @@ typedef struct SphOptions {
                              global box is boxDim x boxDim x nz_cells*h                  */
     int32_t ghost_capacity; /* slab mode: max ghost particles per side (0 = capacity/4)     */
     int32_t emig_capacity;  /* slab mode: max emigrants per side and step (0 = capacity/16) */
-    int32_t reserved[5];
+    int32_t pipeline_readback; /* 1: sph_step() overlaps the device->host copy of step k with the
+                             computation of step k+1 (started speculatively before sph_step
+                             returns).  Positions handed out are exactly those of the blocking
+                             mode; the simulator's internal state runs one step ahead, so the
+                             state getters and sph_push() refer to step k+1.  Meant for loops that
+                             only call sph_step()/sph_positions_host() (`-m time`-like).       */
+    int32_t reserved[4];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */

@@ -291,3 +291,22 @@ def test_mask_handoff_is_bitwise_neutral():
         sim.close()
     for a, b in zip(out[0], out[1]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_pipelined_readback_hands_out_identical_positions():
+    """SphOptions.pipeline_readback overlaps the D2H of step k with the computation of step
+    k+1; every sph_step() must still return exactly the positions of the blocking mode."""
+    pos, vel = random_state(60000, seed=23, lo=2.0, hi=6.0, vel_scale=1.5)
+    seqs = []
+    for pipe in (False, True):
+        sim = sph.Simulator(sph.Settings(numParticles=len(pos)), pipeline_readback=pipe)
+        sim.setup()
+        sim.set_state(pos, vel)
+        frames = []
+        for _ in range(8):
+            sim.simulate()
+            frames.append(sim.getPosition().copy())
+        seqs.append(frames)
+        sim.close()
+    for a, b in zip(*seqs):
+        np.testing.assert_array_equal(a, b)
