@@ -481,8 +481,56 @@ def run_ours(args, wl, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_variants(args, wl):
+    """BASELINE.json configs[1]: neighbour search of this repo against all three reference variants
+    on one GPU -- the real lock-free linked lists, and the two sorted variants RECONSTRUCTED from the
+    README (their source is not in the reference tree; parity unpinned)."""
+    import ctypes
+    import torch
+    import cudafluidsimulator_b200 as sph
+    from oracle.oracle import RECON_SO, REF_SO, ReconSim, RefSim
+    torch.cuda.init()
+    kw = dict(boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"], randomInit=wl["randomInit"])
+    n, steps = wl["n"], args.steps
+    rows = {}
+
+    def buckets_row(b, label):
+        rows[label] = {"grid_ms": 1e3 * b[0] / steps, "sph_update_ms": 1e3 * b[1] / steps,
+                       "transfer_ms": 1e3 * b[2] / steps,
+                       "particle_updates_per_s": n * steps / (b[0] + b[1])}
+    if REF_SO.exists():
+        r = RefSim(n, **kw)
+        for _ in range(steps):
+            b, _ = r.step_timed()
+        buckets_row(b, "reference linked lists (main branch, unmodified)")
+        r.close()
+    if RECON_SO.exists():
+        for morton, label in ((False, "index_sort (RECONSTRUCTED from README, not reference source)"),
+                              (True, "z_index_sort (RECONSTRUCTED from README, not reference source)")):
+            r = ReconSim(n, morton, **kw)
+            for _ in range(steps):
+                b = r.step_timed()
+            buckets_row(b, label)
+            r.close()
+    for mode, label in ((sph.SPH_KEY_FLAT, "this repo, flat keys"), (sph.SPH_KEY_MORTON, "this repo, Morton keys")):
+        ctypes.CDLL("libc.so.6").srand(1)
+        sim = sph.Simulator(sph.Settings(numParticles=n, randomInit=wl["randomInit"], boxDim=wl["boxDim"],
+                                         numCellsPerDim=wl["numCellsPerDim"]), key_mode=mode)
+        sim.setup()
+        t = sph.Times()
+        for _ in range(steps):
+            sim.simulateAndTime(t)
+        buckets_row((t.buildGrid, t.sphUpdate, t.memcpy), label)
+        sim.close()
+    print(json.dumps({"comparison": "neighbour-search variants, simulateAndTime() buckets (host wall clock, "
+                                    "launch + sync inside each bucket, as the reference measures them)",
+                      "workload": args.workload, "n": n, "steps": steps, "variants": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--compare-variants", action="store_true",
+                    help="config 2: time the three reference neighbour-search variants beside this repo")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
@@ -494,7 +542,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.compare_variants:
+        if rank == 0:
+            run_variants(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:
         run_ours(args, wl, rank, local_rank, world)

@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libsph_b200.so"
+# SPH_B200_LIB selects another build of the same ABI (e.g. the self-checking one)
+LIB_PATH = Path(os.environ.get("SPH_B200_LIB", PKG / "libsph_b200.so"))
 
 SPH_KEY_FLAT = 0
 SPH_KEY_MORTON = 1
@@ -96,6 +99,7 @@ SYMBOLS = {
     "sph_slab_buffers": (C.c_int, [_P, C.POINTER(SphSlabBuffers)]),
     "sph_slab_download": (C.c_int, [_P, _U, _F, _F, _I]),
     "sph_set_stream": (C.c_int, [_P, C.c_void_p]),
+    "sph_debug_flags": (C.c_int, [_P, _U, _I]),
     "sph_profile_enable": (C.c_int, [_P, C.c_int]),
     "sph_profile_read": (C.c_int, [_P, _D, C.POINTER(C.c_int64), C.c_int]),
     "sph_stage_name": (C.c_char_p, [C.c_int]),

@@ -53,12 +53,20 @@ def _run(cmd, **kw):
     subprocess.run([str(c) for c in cmd], check=True, **kw)
 
 
-def build_library(force: bool = False, verbose_ptxas: bool = False) -> Path:
+LIB_CHECKED = PKG / "libsph_b200_checked.so"
+
+
+def build_library(force: bool = False, verbose_ptxas: bool = False, checked: bool = False) -> Path:
+    """checked=True: the self-checking variant (-DSPH_BOUNDS_CHECK), same ABI, loaded through
+    SPH_B200_LIB; used by tests/test_gpu_checked_build.py in place of compute-sanitizer."""
     deps = [CSRC / f for f in CU_SOURCES] + list(CSRC.glob("*.cuh")) + [INCLUDE / "sph_b200.h"]
-    if force or _stale(LIB, deps):
+    target = LIB_CHECKED if checked else LIB
+    if force or _stale(target, deps):
         flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else [])
-        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", LIB, *[CSRC / f for f in CU_SOURCES]])
-    return LIB
+        if checked:
+            flags.append("-DSPH_BOUNDS_CHECK")
+        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", target, *[CSRC / f for f in CU_SOURCES]])
+    return target
 
 
 def build_cli(force: bool = False) -> Path:
@@ -86,3 +94,5 @@ def build_all(force: bool = False, oracle: bool = False) -> None:
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, oracle="--oracle" in sys.argv)
+    if "--checked" in sys.argv:
+        build_library(checked=True)

@@ -137,7 +137,7 @@ void enqueue_build(sph_sim *s) {
     s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], s->p.n, s->passes,
                                      s->d.sort_scratch, s->sm_count, s->stream, &hooks);
     stage_begin(s, kStReorder);
-    launch_reorder(s->p, s->d, s->sorted_buf, s->sm_count, s->stream);
+    launch_reorder(s->p, s->d, s->sorted_buf, s->p.n, s->sm_count, s->stream);
     stage_end(s);
 }
 // "update": the reference's "SPH update" bucket.
@@ -332,6 +332,7 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
     p.key_mode = s->opt.key_mode;
     p.slab = 0; p.slot0 = 0; p.zoff = 0; p.ncz = nc; p.zlo = 0; p.zhi = nc; p.nz = nc;
     p.hi_z = p.hi; p.dead_key = 0xffffffffu;
+    p.slot_begin = 0; p.slot_end = p.n; p.dbg = nullptr;
     if (s->opt.z_cell_hi > s->opt.z_cell_lo) {   // slab mode
         const int nz = s->opt.nz_cells > 0 ? s->opt.nz_cells : nc;
         if (p.key_mode != SPH_KEY_FLAT || s->opt.z_cell_lo < 0 || s->opt.z_cell_hi > nz) {
@@ -470,6 +471,8 @@ int sph_setup(sph_sim *s) {
     }
     CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
+    CU(cudaMalloc(&s->p.dbg, sizeof(uint32_t)));
+    CU(cudaMemset(s->p.dbg, 0, sizeof(uint32_t)));
     if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
     if (s->p.key_mode == SPH_KEY_FLAT) {
         CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2) * sizeof(float4)));
@@ -871,7 +874,7 @@ int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
     }
     p.n = n_live;   // emigrated particles carry dead_key and sit behind the live ones
     stage_begin(s, kStReorder);
-    launch_reorder(p, s->d, s->sorted_buf, s->sm_count, s->stream);
+    launch_reorder(p, s->d, s->sorted_buf, n_sort, s->sm_count, s->stream);
     stage_end(s);
     // slot ranges of the lowest (local layer 1) and highest (local layer ncz-2) owned layers
     const uint32_t *cs = s->d.cell_start;
@@ -894,6 +897,8 @@ int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
     REQUIRE_SLAB(s);
     if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
         return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
+    s->p.slot_begin = s->p.slot0 - g_lo;
+    s->p.slot_end = s->p.slot0 + s->p.n + g_hi;
     const Params &p = s->p;
     const uint32_t nn = (uint32_t)p.nc * p.nc;
     stage_begin(s, kStReorder);
@@ -959,6 +964,19 @@ int sph_slab_download(sph_sim *s, uint32_t *ids, float *pos, float *vel, int *n_
         ++m;
     }
     if (n_out) *n_out = m;
+    return 0;
+}
+
+int sph_debug_flags(sph_sim *s, uint32_t *flags, int *checked_build) {
+    REQUIRE_SETUP(s);
+    if (!flags) return fail(SPH_E_INVALID, "null argument");
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(flags, s->p.dbg, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+#ifdef SPH_BOUNDS_CHECK
+    if (checked_build) *checked_build = 1;
+#else
+    if (checked_build) *checked_build = 0;
+#endif
     return 0;
 }
 

@@ -43,7 +43,25 @@ struct Params {
     int nz;         // global cells along z
     float hi_z;     // global box length along z minus h (z wall)
     uint32_t dead_key;  // slab: key given to emigrated particles; sorts behind every live key
+    // -- self-checking build (-DSPH_BOUNDS_CHECK; compute-sanitizer is closed on the GPU pool)
+    int slot_begin, slot_end;   // sorted slots that hold particles this step (ghosts included)
+    uint32_t *dbg;              // violation bits are OR-ed in here (see SPH_DBG_* below)
 };
+
+// Violation bits of the self-checking build, read back with sph_debug_flags().
+enum : uint32_t {
+    SPH_DBG_RUN_BOUNDS = 1u,    // a stencil run [s, e) is reversed or leaves the valid slot range
+    SPH_DBG_TABLE_INDEX = 2u,   // a cell_start index beyond the table
+    SPH_DBG_GATHER_INDEX = 4u,  // a sorted pair points outside the particle arrays
+    SPH_DBG_MASK_WORDS = 8u,    // more mask words than kMaskWords were about to be written / read
+    SPH_DBG_EMIGRANT = 16u,     // emigrant slot beyond the buffer (counted as overflow, not written)
+};
+
+#ifdef SPH_BOUNDS_CHECK
+#define SPH_CHECK(p, cond, bit) do { if (!(cond) && (p).dbg) atomicOr((p).dbg, (bit)); } while (0)
+#else
+#define SPH_CHECK(p, cond, bit) do { } while (0)
+#endif
 
 // ---- cell coordinates and keys ------------------------------------------------
 // ref: simulator.cu:57-76 getGridCell: IEEE divide by h, truncate toward zero.

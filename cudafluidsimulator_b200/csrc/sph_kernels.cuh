@@ -43,7 +43,8 @@ struct Thresholds {
 };
 
 void launch_hash(const Params &p, const DeviceState &d, cudaStream_t s);
-void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int sm_count, cudaStream_t s);
+void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int n_sorted, int sm_count,
+                    cudaStream_t s);
 void launch_density(const Params &p, const Thresholds &t, const DeviceState &d, bool counts,
                     cudaStream_t s);
 void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);

@@ -191,6 +191,12 @@ class Simulator:
         N.check(self._lib.sph_get_stats(self._h, C.byref(ke), C.byref(mr)))
         return ke.value, mr.value
 
+    def debug_flags(self):
+        """(violation bits, is_checked_build) of the self-checking build."""
+        f, c = C.c_uint32(), C.c_int()
+        N.check(self._lib.sph_debug_flags(self._h, C.byref(f), C.byref(c)))
+        return int(f.value), bool(c.value)
+
     def profile_enable(self, on: bool = True) -> None:
         N.check(self._lib.sph_profile_enable(self._h, 1 if on else 0))
 

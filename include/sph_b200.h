@@ -202,6 +202,12 @@ int sph_slab_download(sph_sim *sim, uint32_t *ids, float *pos, float *vel, int *
  * stream, so that NCCL transfers and kernels are ordered without extra events). */
 int sph_set_stream(sph_sim *sim, void *cuda_stream);
 
+/* Self-checking build (nvcc -DSPH_BOUNDS_CHECK, `python -m cudafluidsimulator_b200.build
+ * --checked`): every data-dependent index of the hot kernels is verified on the device and
+ * violations are OR-ed into *flags (bit meanings: SPH_DBG_* in csrc/sph_common.cuh).  In the
+ * normal build *flags stays 0 and *checked_build is 0. */
+int sph_debug_flags(sph_sim *sim, uint32_t *flags, int *checked_build);
+
 /* --- measurement -------------------------------------------------------------
  * Per-kernel CUDA-event times (ms, summed since the last reset) for the stages
  * hash, histogram, sort passes, reorder+cell ranges, density, force+integrate.

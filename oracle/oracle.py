@@ -19,6 +19,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 ORACLE_SO = HERE / "liboracle.so"
 REF_SO = HERE / "_ref" / "libsph_ref.so"
+RECON_SO = HERE / "_ref" / "libsph_recon.so"
 
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int32)
@@ -253,4 +254,45 @@ class RefSim:
     def close(self):
         if self.h:
             self.L.ref_destroy(self.h)
+            self.h = None
+
+
+class ReconSim:
+    """RECONSTRUCTED `index_sort` (morton=False) / `z_index_sort` (morton=True) variants of the
+    reference (oracle/recon_variants.cu; source absent from the reference tree -- reconstructed
+    from README.md:5, parity unpinned).  Benchmark comparator only."""
+
+    def __init__(self, n, morton, *, h=0.1, boxDim=10.0, numCellsPerDim=100.0, timestep=0.01,
+                 randomInit=False):
+        if not RECON_SO.exists():
+            raise FileNotFoundError(f"{RECON_SO} missing: run `make -C oracle` where /root/reference is mounted")
+        L = C.CDLL(str(RECON_SO))
+        self.L = L
+        L.recon_create.restype = C.c_void_p
+        L.recon_create.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_float] * 6
+        L.recon_step_timed.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.recon_positions.restype = _F
+        L.recon_positions.argtypes = [C.c_void_p]
+        L.recon_destroy.argtypes = [C.c_void_p]
+        hh, pi = np.float32(h), np.float32(3.14159265)
+        vk = float(np.float32(45.0) / (pi * np.float32(math.pow(float(hh), 6))))
+        dk = float(np.float32(315.0) / (np.float32(64.0) * pi * np.float32(math.pow(float(hh), 9))))
+        self.n = int(n)
+        self.h = L.recon_create(int(morton), int(randomInit), self.n, h, vk, dk, boxDim, numCellsPerDim, timestep)
+        if not self.h:
+            raise RuntimeError("recon_create failed (no GPU?)")
+        self.buckets = (C.c_double * 3)(0, 0, 0)
+
+    def step_timed(self):
+        rc = self.L.recon_step_timed(self.h, self.buckets)
+        if rc:
+            raise RuntimeError(f"recon_step_timed failed with CUDA error {rc}")
+        return tuple(self.buckets)
+
+    def positions(self):
+        return np.ctypeslib.as_array(self.L.recon_positions(self.h), shape=(self.n, 3)).copy()
+
+    def close(self):
+        if self.h:
+            self.L.recon_destroy(self.h)
             self.h = None

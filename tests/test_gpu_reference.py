@@ -135,3 +135,21 @@ def test_mouse_push_vs_reference():
     sim.close()
     assert not np.any(np.abs(r["vel"] - v1) > 1.0)
     assert (np.abs(r["vel"][:, 2]) > 4).sum() > 0
+
+
+@pytest.mark.parametrize("morton", [False, True], ids=["index_sort", "z_index_sort"])
+def test_reconstructed_sorted_variants_agree_with_reference(morton):
+    """The benchmark comparators (reconstructed from README.md:5, source absent) must at least be
+    the same physics: 20 steps of `-n 20000 -i random` against the real linked-list reference."""
+    from oracle.oracle import RECON_SO, ReconSim
+    if not RECON_SO.exists():
+        pytest.skip("oracle/_ref/libsph_recon.so not built")
+    n = 20000
+    ref = RefSim(n, randomInit=True)
+    rec = ReconSim(n, morton, randomInit=True)
+    for _ in range(20):
+        ref.step()
+        rec.step_timed()
+    np.testing.assert_allclose(rec.positions(), ref.positions(), rtol=2e-4, atol=2e-4)
+    ref.close()
+    rec.close()
