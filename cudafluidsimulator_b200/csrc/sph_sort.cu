@@ -19,13 +19,28 @@
 // running predecessor tile; it stays short only while
 //   (resident tiles / tile time) x (latency of one step) / window  <<  1.
 #ifndef SORT_CTAS_PER_SM
-#define SORT_CTAS_PER_SM 3
+#define SORT_CTAS_PER_SM 4
 #endif
 #ifndef SORT_LOOKBACK_WINDOW
-#define SORT_LOOKBACK_WINDOW 16
+#define SORT_LOOKBACK_WINDOW 4
+#endif
+#ifndef SORT_USE_MATCH_INSTRUCTION
+#define SORT_USE_MATCH_INSTRUCTION 0
 #endif
 #ifndef SORT_SPIN_SLEEP_NS
 #define SORT_SPIN_SLEEP_NS 0
+#endif
+
+#ifdef SORT_TRACE
+__device__ unsigned long long *g_sort_trace;   // [tile][8]: t_start, t_loaded, t_ranked, t_published, t_looked, t_end, smid, walk
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot) do { if (threadIdx.x == 0 && g_sort_trace) g_sort_trace[(size_t)tile * 8 + (slot)] = gtime(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
 #endif
 
 namespace sph {
@@ -49,6 +64,9 @@ __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
 // MATCH.ANY instruction computes the same thing but at a small fraction of the ballot
 // rate -- measured: the pass ran at IPC 0.9 with its warps parked on the match results.)
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+#if SORT_USE_MATCH_INSTRUCTION
+    return __match_any_sync(0xffffffffu, d);
+#endif
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int bit = 0; bit < 8; ++bit) {
@@ -151,6 +169,7 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
                uint32_t *__restrict__ ticket) {     // zeroed
     __shared__ uint64_t s_pairs[kSortTile];                 // 32 KB
     __shared__ uint32_t s_whist[kSortWarps][kRadix];        // 8 KB
+    __shared__ uint32_t s_count[kRadix];
     __shared__ uint32_t s_dstart[kRadix];
     __shared__ uint32_t s_goff[kRadix];
     __shared__ uint32_t s_scan[8];
@@ -162,8 +181,10 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) s_whist[w][tid] = 0;
+    s_count[tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    TRACE(0);
     const int base = (int)tile * kSortTile;
     const int tile_valid = min(kSortTile, n - base);
 
@@ -181,33 +202,57 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
         item[k] = v;
     }
 
+    TRACE(1);
+    // -- early counts: the tile's digit histogram, published BEFORE the (much slower) ranking.
+    // Every later tile needs this aggregate for its look-back; tiles sharing an SM finish their
+    // ranking at very different times (3.8 / 6.2 / 9.4 us for the 1st / 2nd / 3rd resident CTA,
+    // profiles/r01_sort_trace.txt), and with the aggregate published only after ranking every
+    // tile waited for the slowest running predecessor.
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t d = (uint32_t)(item[k] >> (32 + shift)) & 255u;
+        const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, d == d0)) {          // warp-uniform digit (nearly sorted input)
+            if (lane == 0) atomicAdd(&s_count[d0], 32u);
+        } else {
+            atomicAdd(&s_count[d], 1u);
+        }
+    }
+    __syncthreads();
+    const int d = tid;  // kSortThreads == kRadix: thread d owns digit d
+    const uint32_t count = s_count[d];
+    uint32_t *my_status = status + (size_t)tile * kRadix + d;
+    st_relaxed(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
+    TRACE(2);
+
     // -- stable rank of every item among equal digits of its warp ---------------
     // A batch of independent peer masks first, then the (serial, shared-memory) counter
     // updates of that batch.
     uint32_t rank[kSortItems];
-    constexpr int kBatch = 8;
 #if defined(SORT_EXP) && (SORT_EXP & 2)   // microbenchmark only: no ranking (wrong result)
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) rank[k] = 0;
-    if (lane == 0) s_whist[warp][item[0] >> (32 + shift) & 255u] = 0;
 #else
+    constexpr int kBatch = 8;
 #pragma unroll
     for (int k0 = 0; k0 < kSortItems; k0 += kBatch) {
         uint32_t peers[kBatch];
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-            const uint32_t d = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
-            peers[j] = match_digit(d);
+            const uint32_t dd = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, dd, 0);
+            // warp-uniform digit: everyone is everyone's peer, no need for eight ballots
+            peers[j] = __all_sync(0xffffffffu, dd == d0) ? 0xffffffffu : match_digit(dd);
         }
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-            const uint32_t d = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
+            const uint32_t dd = (uint32_t)(item[k0 + j] >> (32 + shift)) & 255u;
             const int leader = __ffs(peers[j]) - 1;
             const uint32_t below = __popc(peers[j] & ((1u << lane) - 1u));
             uint32_t old = 0;
             if (lane == leader) {
-                old = s_whist[warp][d];
-                s_whist[warp][d] = old + __popc(peers[j]);
+                old = s_whist[warp][dd];
+                s_whist[warp][dd] = old + __popc(peers[j]);
             }
             old = __shfl_sync(0xffffffffu, old, leader);
             rank[k0 + j] = old + below;
@@ -217,18 +262,17 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
 #endif
     __syncthreads();
 
-    // -- per-digit: scan over warps, tile count, look-back -----------------------
-    const int d = tid;  // kSortThreads == kRadix
-    uint32_t count = 0;
+    // -- per-digit: exclusive scan of the warp counters -----------------------------
+    {
+        uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = s_whist[w][d];
-        s_whist[w][d] = count;  // exclusive over warps
-        count += c;
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = s_whist[w][d];
+            s_whist[w][d] = run;  // exclusive over warps
+            run += c;
+        }
     }
-    uint32_t *my_status = status + (size_t)tile * kRadix + d;
-    st_relaxed(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
-
+    TRACE(3);
     uint32_t total;
     const uint32_t dstart = block_exclusive_scan_256(count, s_scan, total);
     const uint32_t gbase = block_exclusive_scan_256(__ldg(ghist + d), s_scan, total);
@@ -275,6 +319,10 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     s_dstart[d] = dstart;
     s_goff[d] = gbase + excl - dstart;  // global slot = s_goff[digit] + slot in sorted tile
     __syncthreads();
+    TRACE(4);
+#ifdef SORT_TRACE
+    if (tid == 0 && g_sort_trace) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_sort_trace[(size_t)tile * 8 + 6] = sm; }
+#endif
 
     // -- scatter into tile-sorted order in shared memory -------------------------
 #pragma unroll
@@ -302,6 +350,7 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
 #endif
         }
     }
+    TRACE(5);
 }
 
 }  // namespace
