@@ -247,6 +247,11 @@ def run_slabs(args, wl, rank, local_rank, world):
         # two lattice points fewer per slab than the N=1 box: keeps (owned + 2 ghost) layers x nc^2
         # below 2^24 keys, i.e. the same three 8-bit sort passes as on one GPU
         nlz = (nl - 2) * world
+        if args.scaling == "strong":
+            # BASELINE.json configs[3]: a fixed global problem (default 64M particles, the dam-break
+            # slab stretched 8 box lengths along z) split over however many GPUs there are
+            nlz = (nl - 2) * 8
+            planes = int(np.ceil(args.total / (nl * nlz)))
         zs = h32 + sp * np.arange(nlz, dtype=np.float32)
         nz = int(np.floor(zs[-1] / h32)) + 2                                       # + wall layer
         ranges = slab_ranges(nz, world)
@@ -280,7 +285,9 @@ def run_slabs(args, wl, rank, local_rank, world):
             fn()
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        local_ms = e0.elapsed_time(e1)
+        timed.local_ms = local_ms
+        t = torch.tensor([local_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -293,17 +300,31 @@ def run_slabs(args, wl, rank, local_rank, world):
         ms = timed(drv.step, args.steps)
     launches = b.launch_count - l0
     per_rank = [None] * world
-    dist.all_gather_object(per_rank, {"rank": rank, **drv.last, **{k: v for k, v in drv.stats.items()}})
+    dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": timed.local_ms / args.steps, **drv.last,
+                                      **{k: v for k, v in drv.stats.items()}})
     b.close()
 
     # -- e2e: every step also copies the owned particles' positions to pinned host memory --
     b, drv = make()
     host = torch.empty((b.capacity, 4), dtype=torch.float32).pin_memory()
+    stage = torch.empty((b.capacity, 4), dtype=torch.float32, device=b.device)
+    copy_stream = torch.cuda.Stream()
+    copy_done = torch.cuda.Event()
+    copy_done.record()
+
     def step_e2e():
+        # every step's owned positions reach pinned host memory; the PCIe copy of step k runs on a
+        # side stream from a device staging copy while step k+1 computes
         drv.step()
         k = drv.last["n_owned"]
-        host[:k].copy_(b.cur_pos[:k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        copy_done.synchronize()                  # staging buffer free again
+        stage[:k].copy_(b.cur_pos[:k])
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            host[:k].copy_(stage[:k], non_blocking=True)
+            copy_done.record()
     for _ in range(args.warmup):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
@@ -314,7 +335,7 @@ def run_slabs(args, wl, rank, local_rank, world):
         line = {
             "metric": "particle-updates/s", "value": n_glob * args.steps / (ms * 1e-3),
             "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_per_gpu": n_glob // world, "n_total": n_glob, "boxDim": wl["boxDim"],
                        "numCellsPerDim": wl["numCellsPerDim"], "global_cells_z": nz,
@@ -326,10 +347,12 @@ def run_slabs(args, wl, rank, local_rank, world):
             "e2e": {"value": n_glob * args.steps / (e2e_ms * 1e-3), "unit": "particle-updates/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n_glob * 16,
-                    "api": "SlabDriver.step() + per-step D2H of every owned particle's position record into pinned host memory"},
+                    "api": "SlabDriver.step() + per-step D2H of every owned particle's position record into pinned host "
+                           "memory (copy of step k overlaps the computation of step k+1)"},
             "gpu_launches": int(launches) * world,
             "load_balance": {"owned_per_rank": owned, "imbalance_max_over_mean": max(owned) / (sum(owned) / world),
                              "ghosts_last_step": [r["ghosts"] for r in per_rank],
+                             "ms_per_step_per_rank": [round(r["ms_per_step"], 4) for r in per_rank],
                              "migrated_total": [r["migrated_particles"] for r in per_rank]},
         }
         print(json.dumps(line), flush=True)
@@ -538,6 +561,9 @@ def main():
     ap.add_argument("--workload", default="16m_grid", choices=list(WORKLOADS))
     ap.add_argument("--key", default="flat", choices=["flat", "morton"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
+    ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

@@ -61,7 +61,7 @@ class SphSlabInfo(C.Structure):
 class SphSlabBuffers(C.Structure):
     _fields_ = [("srt_pos", C.c_void_p), ("srt_vel", C.c_void_p), ("pa", C.c_void_p),
                 ("cur_pos", C.c_void_p), ("cur_vel", C.c_void_p),
-                ("emig_pos", C.c_void_p * 2), ("emig_vel", C.c_void_p * 2),
+                ("emig_pos", C.c_void_p * 2), ("emig_vel", C.c_void_p * 2), ("counts", C.c_void_p),
                 ("capacity", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32)]
 
 
@@ -93,6 +93,10 @@ SYMBOLS = {
     "sph_get_stats": (C.c_int, [_P, _D, _D]),
     "sph_slab_load": (C.c_int, [_P, C.c_int, _F, _F, _U]),
     "sph_slab_build": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
+    "sph_slab_build_async": (C.c_int, [_P]),
+    "sph_slab_build_finish": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
+    "sph_slab_force_async": (C.c_int, [_P]),
+    "sph_slab_force_finish": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
     "sph_slab_density": (C.c_int, [_P, C.c_int, C.c_int]),
     "sph_slab_force": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
     "sph_slab_append": (C.c_int, [_P, C.c_int]),

@@ -72,10 +72,14 @@ struct sph_sim {
     int n_dead = 0;             // of which emigrated (dropped by the next build)
     int hashed_upto = 0;        // keys of cur[0, hashed_upto) are valid
     int slab_overflow = 0;
+    uint32_t *slab_counts = nullptr;       // device: [0..3] boundary-layer slot bounds, [4..5] emigrant counts
+    uint32_t *slab_counts_host = nullptr;  // pinned mirror, filled asynchronously
+    int pending_n_sort = 0, pending_n_live = 0;
     bool keys_valid = false;    // d.key matches d.cur_pos
     bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
     cudaGraphExec_t graph = nullptr;       // step graph writing out_buf[0]
     cudaGraphExec_t graph_alt = nullptr;   // same step writing out_buf[1] (pipelined readback)
+    cudaGraphExec_t graph_build = nullptr, graph_update = nullptr;   // the two halves, for the timed step
     float *out_buf[2] = {nullptr, nullptr};
     int out_parity = 0;
     bool spec_inflight = false;            // a step is enqueued whose positions were not handed out yet
@@ -186,6 +190,39 @@ int enqueue_step(sph_sim *s) {
     return 0;
 }
 
+// One half of the step ("Grid construction" or "SPH update" bucket) as a graph replay: at small N
+// the step is launch-bound (hist + 3 passes + reorder = 6 launches for ~30 us of work).
+int enqueue_half(sph_sim *s, bool build) {
+    const bool want_graph = s->opt.use_graph != 2 && !s->profiling && s->keys_valid;
+    if (!want_graph) {
+        if (build) enqueue_build(s); else enqueue_update(s);
+        return 0;
+    }
+    cudaGraphExec_t &slot = build ? s->graph_build : s->graph_update;
+    const int64_t l0 = s->launches;
+    int64_t sl0[SPH_STAGE_COUNT];
+    memcpy(sl0, s->stage_launches, sizeof(sl0));
+    if (!slot) {
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        if (build) enqueue_build(s); else enqueue_update(s);
+        CU(cudaStreamEndCapture(s->stream, &g));
+        CU(cudaGraphInstantiate(&slot, g, 0));
+        cudaGraphDestroy(g);
+        s->launches = l0;
+        memcpy(s->stage_launches, sl0, sizeof(sl0));
+    }
+    CU(cudaGraphLaunch(slot, s->stream));
+    if (build) {
+        s->launches += 2 + s->passes;
+        s->stage_launches[kStHist] += 1; s->stage_launches[kStSort] += s->passes; s->stage_launches[kStReorder] += 1;
+    } else {
+        s->launches += 2;
+        s->stage_launches[kStDensity] += 1; s->stage_launches[kStForce] += 1;
+    }
+    return 0;
+}
+
 int sync_stream(sph_sim *s) {
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
@@ -196,7 +233,9 @@ int sync_stream(sph_sim *s) {
 void drop_graph(sph_sim *s) {
     if (s->graph) cudaGraphExecDestroy(s->graph);
     if (s->graph_alt) cudaGraphExecDestroy(s->graph_alt);
-    s->graph = s->graph_alt = nullptr;
+    if (s->graph_build) cudaGraphExecDestroy(s->graph_build);
+    if (s->graph_update) cudaGraphExecDestroy(s->graph_update);
+    s->graph = s->graph_alt = s->graph_build = s->graph_update = nullptr;
 }
 
 float bisect_sqrt_threshold(float target, bool smallest_ge) {
@@ -446,8 +485,10 @@ int sph_setup(sph_sim *s) {
             CU(cudaMalloc(&d.emig_pos[sd], (size_t)d.emig_capacity * sizeof(float4)));
             CU(cudaMalloc(&d.emig_vel[sd], (size_t)d.emig_capacity * sizeof(float4)));
         }
-        CU(cudaMalloc(&d.emig_count, 2 * sizeof(uint32_t)));
-        CU(cudaMemset(d.emig_count, 0, 2 * sizeof(uint32_t)));
+        CU(cudaMalloc(&s->slab_counts, 8 * sizeof(uint32_t)));
+        CU(cudaMemset(s->slab_counts, 0, 8 * sizeof(uint32_t)));
+        CU(cudaMallocHost(&s->slab_counts_host, 8 * sizeof(uint32_t)));
+        d.emig_count = s->slab_counts + 4;
     }
     CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
     CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
@@ -550,15 +591,17 @@ int sph_step_timed(sph_sim *s, SphTimes *times) {
         return std::chrono::duration_cast<std::chrono::duration<double>>(clk::now() - a).count();
     };
     if (s->p.n > 0) {
+        s->d.out_pos = s->out_buf[0];
+        s->out_parity = 0;
         auto t0 = clk::now();
-        enqueue_build(s);
-        int rc = sync_stream(s);
+        int rc = enqueue_half(s, true);
+        if (rc == 0) rc = sync_stream(s);
         if (rc) return rc;
         times->buildGrid += secs(t0);
 
         auto t1 = clk::now();
-        enqueue_update(s);
-        rc = sync_stream(s);
+        rc = enqueue_half(s, false);
+        if (rc == 0) rc = sync_stream(s);
         if (rc) return rc;
         times->sphUpdate += secs(t1);
         s->step_valid = true;
@@ -818,6 +861,7 @@ int sph_slab_buffers(sph_sim *s, SphSlabBuffers *out) {
     out->srt_pos = d.srt_pos; out->srt_vel = d.srt_vel; out->pa = d.pa;
     out->cur_pos = d.cur_pos; out->cur_vel = d.cur_vel;
     for (int sd = 0; sd < 2; ++sd) { out->emig_pos[sd] = d.emig_pos[sd]; out->emig_vel[sd] = d.emig_vel[sd]; }
+    out->counts = s->slab_counts;
     out->capacity = s->capacity; out->ghost_capacity = s->ghost_cap; out->emig_capacity = d.emig_capacity;
     return 0;
 }
@@ -852,15 +896,15 @@ int sph_slab_append(sph_sim *s, int count) {
     return 0;
 }
 
-int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
+// Enqueue only: hash of new arrivals, sort, reorder; the four slot bounds of the two boundary
+// layers land in slab_counts[0..3] (device, for sending to the neighbours without a host round
+// trip) and, asynchronously, in the pinned mirror read by sph_slab_build_finish().
+int sph_slab_build_async(sph_sim *s) {
     REQUIRE_SLAB(s);
-    if (!info) return fail(SPH_E_INVALID, "null argument");
-    memset(info, 0, sizeof(*info));
     Params &p = s->p;
     const int n_sort = s->n_total;
     const int n_live = s->n_total - s->n_dead;
     const uint32_t nn = (uint32_t)p.nc * p.nc;
-    uint32_t b[4] = {0, 0, 0, 0};
     if (n_sort > 0) {
         // keys of freshly arrived particles (everything after a load)
         if (s->hashed_upto < n_sort) {
@@ -876,21 +920,37 @@ int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
     stage_begin(s, kStReorder);
     launch_reorder(p, s->d, s->sorted_buf, n_sort, s->sm_count, s->stream);
     stage_end(s);
-    // slot ranges of the lowest (local layer 1) and highest (local layer ncz-2) owned layers
+    // slot bounds of the lowest (local layer 1) and highest (local layer ncz-2) owned layers
     const uint32_t *cs = s->d.cell_start;
-    CU(cudaMemcpyAsync(&b[0], cs + nn, 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&b[1], cs + 2 * nn, 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&b[2], cs + (size_t)nn * (p.ncz - 2), 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&b[3], cs + (size_t)nn * (p.ncz - 1), 4, cudaMemcpyDeviceToHost, s->stream));
+    const size_t at[4] = {nn, 2 * (size_t)nn, (size_t)nn * (p.ncz - 2), (size_t)nn * (p.ncz - 1)};
+    for (int i = 0; i < 4; ++i)
+        CU(cudaMemcpyAsync(s->slab_counts + i, cs + at[i], 4, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->slab_counts_host, s->slab_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    s->pending_n_sort = n_sort;
+    s->pending_n_live = n_live;
+    return 0;
+}
+
+int sph_slab_build_finish(sph_sim *s, SphSlabInfo *info) {
+    REQUIRE_SLAB(s);
+    if (!info) return fail(SPH_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
     int rc = sync_stream(s);
     if (rc) return rc;
+    const uint32_t *b = s->slab_counts_host;
+    const int n_live = s->pending_n_live;
     s->n_total = n_live; s->n_dead = 0; s->hashed_upto = n_live;
-    info->n_owned = n_live; info->n_total = n_live; info->slot0 = p.slot0;
+    info->n_owned = n_live; info->n_total = n_live; info->slot0 = s->p.slot0;
     info->lo_first = (int)b[0]; info->lo_count = (int)(b[1] - b[0]);
     info->hi_first = (int)b[2]; info->hi_count = (int)(b[3] - b[2]);
     if (info->lo_count > s->ghost_cap || info->hi_count > s->ghost_cap) s->slab_overflow |= 2;
     info->overflow = s->slab_overflow;
     return 0;
+}
+
+int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
+    int rc = sph_slab_build_async(s);
+    return rc ? rc : sph_slab_build_finish(s, info);
 }
 
 int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
@@ -916,20 +976,27 @@ int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
     return 0;
 }
 
-int sph_slab_force(sph_sim *s, SphSlabInfo *info) {
+// Enqueue only: force + integrate; emigrant counts land in slab_counts[4..5] (device) and in
+// the pinned mirror.
+int sph_slab_force_async(sph_sim *s) {
     REQUIRE_SLAB(s);
-    if (!info) return fail(SPH_E_INVALID, "null argument");
-    memset(info, 0, sizeof(*info));
-    uint32_t cnt[2] = {0, 0};
     CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
     if (s->p.n > 0) {
         stage_begin(s, kStForce);
         launch_force_integrate(s->p, s->th, s->d, s->stream);
         stage_end(s);
     }
-    CU(cudaMemcpyAsync(cnt, s->d.emig_count, sizeof(cnt), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->d.emig_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+int sph_slab_force_finish(sph_sim *s, SphSlabInfo *info) {
+    REQUIRE_SLAB(s);
+    if (!info) return fail(SPH_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
     int rc = sync_stream(s);
     if (rc) return rc;
+    const uint32_t *cnt = s->slab_counts_host + 4;
     for (int sd = 0; sd < 2; ++sd) {
         if ((int)cnt[sd] > s->d.emig_capacity) s->slab_overflow |= 4;
         info->emig_count[sd] = (int)std::min<uint32_t>(cnt[sd], (uint32_t)s->d.emig_capacity);
@@ -938,6 +1005,11 @@ int sph_slab_force(sph_sim *s, SphSlabInfo *info) {
     info->n_owned = s->p.n - s->n_dead; info->n_total = s->n_total; info->slot0 = s->p.slot0;
     info->overflow = s->slab_overflow;
     return 0;
+}
+
+int sph_slab_force(sph_sim *s, SphSlabInfo *info) {
+    int rc = sph_slab_force_async(s);
+    return rc ? rc : sph_slab_force_finish(s, info);
 }
 
 int sph_slab_download(sph_sim *s, uint32_t *ids, float *pos, float *vel, int *n_out) {

@@ -9,6 +9,9 @@
 //   -k <flat|morton>                cell-key form of the sort
 //   -s <steps>                      iterations in time mode (default 100, main.cpp:69)
 //   -f <frames>                     frames to run in headless free mode (default 600)
+//   -l <file> / -d <file>           load the initial state from / dump the final state to a file
+//                                   (state I/O; the reference has none).  Format: "SPHB200\0",
+//                                   int32 N, N x 3 float32 positions, N x 3 float32 velocities
 // Free mode needs GLUT/OpenGL (ref: display.cpp), which this image does not have; when
 // built without SPH_WITH_GLUT it runs the same per-frame sequence display() does
 // (simulate() + getPosition()) without drawing and reports frames per second.
@@ -21,6 +24,10 @@
 #include <string>
 
 #include "simulator.h"
+#include "sph_b200.h"
+
+#include <cstring>
+#include <vector>
 
 #ifdef SPH_WITH_GLUT
 void startVisualization(Simulator *simulator);  // display.cpp of the caller
@@ -40,6 +47,30 @@ static void usage() {
 
 static bool one_of(const std::string &v, const char *a, const char *b) { return v == a || v == b; }
 
+static const char kMagic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', 0};
+
+static bool load_state(const std::string &path, int n, std::vector<float> &pos, std::vector<float> &vel) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[8];
+    int32_t m = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kMagic, 8) == 0 && fread(&m, 4, 1, f) == 1 && m == n;
+    pos.resize((size_t)3 * n);
+    vel.resize((size_t)3 * n);
+    ok = ok && fread(pos.data(), 4, pos.size(), f) == pos.size() && fread(vel.data(), 4, vel.size(), f) == vel.size();
+    fclose(f);
+    return ok;
+}
+
+static bool dump_state(const std::string &path, int n, const std::vector<float> &pos, const std::vector<float> &vel) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    int32_t m = n;
+    bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(&m, 4, 1, f) == 1 &&
+              fwrite(pos.data(), 4, pos.size(), f) == pos.size() && fwrite(vel.data(), 4, vel.size(), f) == vel.size();
+    return fclose(f) == 0 && ok;
+}
+
 int main(int argc, char **argv) {
     int numParticles = 1000;
     bool randomInit = false;
@@ -48,9 +79,10 @@ int main(int argc, char **argv) {
     float cells = 100;
     int numIters = 100;
     int frames = 600;
+    std::string loadPath, dumpPath;
     int opt;
 
-    while ((opt = getopt(argc, argv, "n:i:m:b:c:k:s:f:?")) != -1) {
+    while ((opt = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:?")) != -1) {
         const std::string arg = optarg ? optarg : "";
         switch (opt) {
         case 'n':
@@ -92,6 +124,12 @@ int main(int argc, char **argv) {
         case 'f':
             frames = std::stoi(arg);
             break;
+        case 'l':
+            loadPath = arg;
+            break;
+        case 'd':
+            dumpPath = arg;
+            break;
         case '?':
             usage();
             return 1;
@@ -110,6 +148,14 @@ int main(int argc, char **argv) {
     Simulator *simulator = new Simulator(&settings);
     simulator->setup();
     if (simulator->status() != 0) return 2;  // the reference would carry on silently
+    if (!loadPath.empty()) {
+        std::vector<float> pos, vel;
+        if (!load_state(loadPath, numParticles, pos, vel) ||
+            sph_set_state(simulator->handle(), pos.data(), vel.data()) != 0) {
+            fprintf(stderr, "sph: cannot load %d particles from %s: %s\n", numParticles, loadPath.c_str(), sph_last_error());
+            return 2;
+        }
+    }
 
     if (benchmark) {
         Times times;
@@ -135,6 +181,14 @@ int main(int argc, char **argv) {
         printf("free mode (headless build, no GLUT): %d frames in %.3f s = %.1f frames/s (checksum %.6f)\n",
                frames, dt, frames / dt, checksum);
 #endif
+    }
+    if (!dumpPath.empty()) {
+        std::vector<float> pos((size_t)3 * numParticles), vel((size_t)3 * numParticles);
+        if (sph_get_state(simulator->handle(), pos.data(), vel.data()) != 0 ||
+            !dump_state(dumpPath, numParticles, pos, vel)) {
+            fprintf(stderr, "sph: cannot dump the state to %s: %s\n", dumpPath.c_str(), sph_last_error());
+            return 2;
+        }
     }
     return 0;
 }

@@ -101,7 +101,8 @@ class SlabBackend:
         self.cur_vel = _tensor(b.cur_vel, b.capacity, 4, dev)
         self.emig_pos = [_tensor(b.emig_pos[i], b.emig_capacity, 4, dev) for i in range(2)]
         self.emig_vel = [_tensor(b.emig_vel[i], b.emig_capacity, 4, dev) for i in range(2)]
-        self.capacity, self.ghost_capacity = b.capacity, b.ghost_capacity
+        self.counts = torch.as_tensor(_DevView(b.counts, 8 * 4), device=dev).view(torch.int32)
+        self.capacity, self.ghost_capacity, self.emig_capacity = b.capacity, b.ghost_capacity, b.emig_capacity
         self.device = dev
 
     def _info(self, i):
@@ -119,6 +120,22 @@ class SlabBackend:
     def build(self):
         i = self.N.SphSlabInfo()
         self.N.check(self.lib.sph_slab_build(self.h, C.byref(i)))
+        return self._info(i)
+
+    def build_async(self):
+        self.N.check(self.lib.sph_slab_build_async(self.h))
+
+    def build_finish(self):
+        i = self.N.SphSlabInfo()
+        self.N.check(self.lib.sph_slab_build_finish(self.h, C.byref(i)))
+        return self._info(i)
+
+    def force_async(self):
+        self.N.check(self.lib.sph_slab_force_async(self.h))
+
+    def force_finish(self):
+        i = self.N.SphSlabInfo()
+        self.N.check(self.lib.sph_slab_force_finish(self.h, C.byref(i)))
         return self._info(i)
 
     def density(self, g_lo, g_hi):
@@ -190,14 +207,40 @@ class SlabDriver:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def _neighbour_counts(self, lo, hi):
+        """My device counts[lo:hi] -> both neighbours, theirs -> a pinned host mirror
+        (row 0 = from below, row 1 = from above); asynchronous, complete after the next
+        synchronisation of the stream."""
+        b = self.b
+        if not hasattr(self, "_nb_dev"):
+            self._nb_dev = torch.zeros((2, 8), dtype=torch.int32, device=b.counts.device)
+            self._nb_host = torch.zeros((2, 8), dtype=torch.int32).pin_memory()
+        mine = b.counts[lo:hi]
+        sends, recvs = [], []
+        if self.down is not None:
+            sends.append((mine, self.down)); recvs.append((self._nb_dev[0, lo:hi], self.down))
+        if self.up is not None:
+            sends.append((mine, self.up)); recvs.append((self._nb_dev[1, lo:hi], self.up))
+        self._exchange(sends, recvs)
+        self._nb_host.copy_(self._nb_dev, non_blocking=True)
+
     # -- one timestep ------------------------------------------------------------------
     def step(self):
         b = self.b
-        info = b.build()
+        fast = hasattr(b, "build_async")   # device-side counts: neighbours only, one sync per phase
+        if fast:
+            b.build_async()
+            self._neighbour_counts(0, 4)
+            info = b.build_finish()
+            nb = self._nb_host
+            g_lo = int(nb[0, 3] - nb[0, 2]) if self.down is not None else 0   # their highest layer
+            g_hi = int(nb[1, 1] - nb[1, 0]) if self.up is not None else 0     # their lowest layer
+        else:
+            info = b.build()
+            counts = self._counts([info.lo_count, info.hi_count])
+            g_lo = counts[self.down][1] if self.down is not None else 0
+            g_hi = counts[self.up][0] if self.up is not None else 0
         n, s0 = info.n_owned, info.slot0
-        counts = self._counts([info.lo_count, info.hi_count])
-        g_lo = counts[self.down][1] if self.down is not None else 0   # their highest layer
-        g_hi = counts[self.up][0] if self.up is not None else 0       # their lowest layer
         if g_lo > b.ghost_capacity or g_hi > b.ghost_capacity:
             raise RuntimeError(f"rank {self.rank}: ghost layer ({g_lo}, {g_hi}) exceeds capacity {b.ghost_capacity}")
         lo = slice(info.lo_first, info.lo_first + info.lo_count)      # my lowest owned layer
@@ -217,12 +260,21 @@ class SlabDriver:
         halo([b.srt_pos, b.srt_vel])          # exchange A
         b.density(g_lo, g_hi)
         halo([b.pa])                           # exchange B
-        f = b.force()
 
         # migration: my emigrants -> neighbours; theirs are appended behind my particles
-        em = self._counts([f.emig_down, f.emig_up])
-        in_dn = em[self.down][1] if self.down is not None else 0
-        in_up = em[self.up][0] if self.up is not None else 0
+        if fast:
+            b.force_async()
+            self._neighbour_counts(4, 6)
+            f = b.force_finish()
+            nb = self._nb_host
+            # (senders cap at their emigrant buffer; all slabs are created with the same capacity)
+            in_dn = min(int(nb[0, 5]), b.emig_capacity) if self.down is not None else 0   # from below, moving up
+            in_up = min(int(nb[1, 4]), b.emig_capacity) if self.up is not None else 0     # from above, moving down
+        else:
+            f = b.force()
+            em = self._counts([f.emig_down, f.emig_up])
+            in_dn = em[self.down][1] if self.down is not None else 0
+            in_up = em[self.up][0] if self.up is not None else 0
         at = f.n_total
         if at + in_dn + in_up > b.capacity:
             raise RuntimeError(f"rank {self.rank}: {at}+{in_dn}+{in_up} particles exceed capacity {b.capacity}")

@@ -84,6 +84,9 @@ class Simulator {
     // additive: last error of the underlying C ABI (0 == ok); the reference has no
     // error reporting at all, so ignoring this reproduces its behaviour
     int status() const { return lastStatus; }
+    // additive: the C-ABI handle, for callers that want the extra entry points of sph_b200.h
+    // (state I/O, parity hooks)
+    sph_sim *handle() const { return impl; }
 
   private:
     int lastStatus = 0;

@@ -186,14 +186,25 @@ typedef struct SphSlabBuffers {   /* device pointers, valid until sph_destroy */
     void *pa;                     /* float2 per sorted slot                  */
     void *cur_pos, *cur_vel;      /* float4 per particle, storage order      */
     void *emig_pos[2], *emig_vel[2]; /* float4 per emigrant, per side        */
+    void *counts;                 /* uint32[8]: [0..3] slot bounds of the lowest / highest owned
+                                     layer (lo_first, lo_end, hi_first, hi_end), [4..5] emigrants
+                                     down / up -- device copies, to be sent to the neighbours
+                                     without a host round trip */
     int32_t capacity, ghost_capacity, emig_capacity;
 } SphSlabBuffers;
 
 /* Replace the owned particle set (host arrays; ids are global particle ids). */
 int sph_slab_load(sph_sim *sim, int n, const float *pos, const float *vel, const uint32_t *ids);
-int sph_slab_build(sph_sim *sim, SphSlabInfo *info);
+int sph_slab_build(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
+/* Split forms: _async only enqueues (the counts also land in SphSlabBuffers.counts on the
+ * device), _finish synchronises once and reports them -- lets the caller overlap the count
+ * exchange with its neighbours with that one synchronisation. */
+int sph_slab_build_async(sph_sim *sim);
+int sph_slab_build_finish(sph_sim *sim, SphSlabInfo *info);
+int sph_slab_force_async(sph_sim *sim);
+int sph_slab_force_finish(sph_sim *sim, SphSlabInfo *info);
 int sph_slab_density(sph_sim *sim, int ghost_lo_count, int ghost_hi_count);
-int sph_slab_force(sph_sim *sim, SphSlabInfo *info);
+int sph_slab_force(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
 int sph_slab_append(sph_sim *sim, int count);
 int sph_slab_buffers(sph_sim *sim, SphSlabBuffers *out);
 /* Owned live particles (after sph_slab_force: the integrated state), any order. */

@@ -1,8 +1,16 @@
 #!/bin/bash
-# usage: gpurun --gpus N -- 'bash scripts/gpu_multi.sh N'
+# usage: gpurun --gpus N -- 'bash scripts/gpu_multi.sh N [extra bench args]'
 set -u
-N=${1:-2}
+N=${1:-2}; shift
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv | head -9
-echo "== nccl slab test"; timeout 600 python -m pytest tests/test_gpu_slab.py -m gpu -q --no-header -rf -p no:cacheprovider -k nccl 2>&1 | tail -8
-echo "== bench N=$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 50 --warmup 3 2>&1 | tail -4 | tee gpurun_out/bench_slab_n$N.json
+run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $1 "${@:2}" 2>&1 | grep '^{' | tail -1; }
+for g in 2 4 8; do
+  [ $g -le $N ] || continue
+  echo "== weak N=$g"; run $g --steps 100 --warmup 3 | tee gpurun_out/scale_weak_n$g.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('value %.3e ms/step %.3f e2e %.3e n_total %d' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['n_total']), d['load_balance'])"
+done
+for g in 2 4 8; do
+  [ $g -le $N ] || continue
+  echo "== strong 64M N=$g"; run $g --steps 50 --warmup 3 --scaling strong | tee gpurun_out/scale_strong_n$g.json | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('value %.3e ms/step %.3f n_total %d' % (d['value'], d['ms_per_step'], d['config']['n_total']), d['load_balance']['owned_per_rank'])"
+done

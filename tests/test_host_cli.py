@@ -86,3 +86,18 @@ def test_cli_extension_flags():
     assert r.returncode == 0, r.stderr
     r = run("-n", "2000000", "-i", "grid", "-m", "time", "-s", "2")   # > 109^3 in the reference box
     assert r.returncode == 2 and "lattice" in r.stderr
+
+
+@pytest.mark.gpu
+def test_state_dump_and_load_round_trip(tmp_path):
+    """-d after 10 steps, then -l + 10 more steps == 20 steps straight (deterministic sort)."""
+    a, b, c = tmp_path / "a.bin", tmp_path / "b.bin", tmp_path / "c.bin"
+    assert run("-n", "5000", "-s", "10", "-d", str(a)).returncode == 0
+    assert run("-n", "5000", "-s", "10", "-l", str(a), "-d", str(b)).returncode == 0
+    assert run("-n", "5000", "-s", "20", "-d", str(c)).returncode == 0
+    import numpy as np
+    fb, fc = np.fromfile(b, np.uint8), np.fromfile(c, np.uint8)
+    assert fb[:8].tobytes() == b"SPHB200\x00" and len(fb) == 12 + 5000 * 24
+    pb, pc = fb[12:].view(np.float32), fc[12:].view(np.float32)
+    np.testing.assert_allclose(pb, pc, rtol=1e-5, atol=1e-5)
+    assert run("-n", "4000", "-l", str(a)).returncode == 2     # particle count mismatch is an error
