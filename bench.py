@@ -440,11 +440,17 @@ def run_ours(args, wl, rank, local_rank, world):
     clk = clocks.summary()
     f_den, f_force, f_int = flops_per_particle(meanC, meanK)
     passes = 3
-    bytes_stage = {  # algorithmic bytes per particle (DESIGN.md section 4)
+    bytes_stage = {  # algorithmic bytes per particle (DESIGN.md section 3)
         "hash": 20, "histogram": 4, "sort_passes": 4 + 8 + 16 * (passes - 1),
-        "reorder_cellstart": 8 + 32 + 32 + 4 * (wl["numCellsPerDim"] ** 3) / n,
-        "density": 16 + 12, "force_integrate": 16 + 16 + 8 + 4 + 16 + 16 + 4 + 12,
+        "reorder_cellstart": 8 + 32 + 32 + 12 + 4 * (wl["numCellsPerDim"] ** 3) / n,
+        "density": 16 + 12 + 8, "force_integrate": 16 + 16 + 8 + 4 + 8 + 16 + 16 + 4 + 12,
     }
+    ncu_kernel = {"density": "k_density_flat<0, 1>", "force_integrate": "k_force_integrate_flat",
+                  "reorder_cellstart": "k_reorder", "sort_passes": "k_onesweep<0>", "histogram": "k_histogram"}
+    traffic = None
+    tfile = ROOT / "profiles" / "r01_traffic.json"
+    if tfile.exists() and args.workload == "16m_grid":
+        traffic = json.loads(tfile.read_text())
     flops_stage = {"density": f_den, "force_integrate": f_force + f_int}
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp32_peak_tflops = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
@@ -462,7 +468,10 @@ def run_ours(args, wl, rank, local_rank, world):
     d = stages[dom]
     if dom in flops_stage:
         roof = {"kernel": dom, "bound": "fp32", "achieved": d["algorithmic_TFLOPs"], "peak": round(fp32_peak_tflops, 2),
-                "unit": "TFLOP/s", "frac": d["fp32_frac"], "traffic": None,
+                "unit": "TFLOP/s", "frac": d["fp32_frac"],
+                "traffic": (traffic["bytes_per_launch"].get(ncu_kernel.get(dom)) if traffic else None),
+                "traffic_source": traffic["source"] if traffic else None,
+                "algorithmic_bytes_per_launch": bytes_stage[dom] * n,
                 "peak_source": f"SMs*128 lanes*2*clocks.max.sm ({sm_count} SMs, {sm_max_mhz:.0f} MHz from "
                                f"MEASURED_PEAKS.json, {peak_kind}); no tensor cores on this path",
                 "flops_per_particle": round(flops_stage[dom], 1), "mean_candidates_C": round(meanC, 2),
@@ -470,7 +479,11 @@ def run_ours(args, wl, rank, local_rank, world):
                 "hbm_frac": d.get("hbm_frac")}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": d["hbm_frac"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"}
+                "frac": d["hbm_frac"],
+                "traffic": (traffic["bytes_per_launch"].get(ncu_kernel.get(dom)) if traffic else None),
+                "traffic_source": traffic["source"] if traffic else None,
+                "algorithmic_bytes_per_launch": bytes_stage[dom] * n,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"}
 
     line = {
         "metric": "particle-updates/s", "value": value, "unit": "particle-updates/s", "n_gpus": world,

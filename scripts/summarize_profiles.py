@@ -76,4 +76,23 @@ for hname in stalls:
         short = hname.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")
         lines.append(f"| {short} | " + " | ".join(f"{v:.2f}" for v in vals) + " |")
 (out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
+
+# per-launch DRAM traffic of every kernel (bench.py reports it as roofline.traffic)
+import json
+
+
+def _bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+traffic = {}
+for r, nm in zip(d2, names):
+    rd = _bytes(r[jx["dram__bytes_read.sum"]], units[jx["dram__bytes_read.sum"]])
+    wr = _bytes(r[jx["dram__bytes_write.sum"]], units[jx["dram__bytes_write.sum"]])
+    traffic.setdefault(nm, []).append(rd + wr)
+(out / f"{tag}_traffic.json").write_text(json.dumps(
+    {"source": f"profiles/{tag}_ncu_summary.md: ncu --set full, one step of the 16M grid workload after 100 steps; "
+               "dram__bytes_read.sum + dram__bytes_write.sum per launch",
+     "bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}}, indent=1) + "\n")
 print("\n".join(lines))
