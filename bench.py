@@ -42,6 +42,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[2]: 16M particles, grid init, scaled box
     "16m_grid": dict(n=16_000_000, randomInit=False, boxDim=25.6, numCellsPerDim=256.0),
+    # BASELINE.json configs[4] per-GPU share: 32M particles (needs a 320-cell box: 283^3 < 32M)
+    "32m_grid": dict(n=32_000_000, randomInit=False, boxDim=32.0, numCellsPerDim=320.0),
     # BASELINE.json configs[1]: 1M particles, random init, reference box
     "1m_random": dict(n=1_000_000, randomInit=True, boxDim=10.0, numCellsPerDim=100.0),
     # BASELINE.json configs[0]: ./sph -n 10000 -i grid -m time
