@@ -1,7 +1,7 @@
 // main.cpp -- the `./sph -n <N> -i <random|grid> -m <free|time>` driver
 // (ref: src/main.cpp:12-83), headless-capable.
 //
-// Flags, defaults and validation are the reference's: -n (default 1000), -i grid,
+// Flags, defaults, messages and exit codes are the reference's: -n (default 1000), -i grid,
 // -m time, -? usage, exit 1 on a bad value; time mode = 100 x simulateAndTime() then
 // displayTimes().  Additive flags (reference behaviour when absent):
 //   -b <boxDim>  -c <cellsPerDim>   scale the domain beyond the hard-coded 10 / 100 box
@@ -20,36 +20,87 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "simulator.h"
 #include "sph_b200.h"
-
-#include <cstring>
-#include <vector>
 
 #ifdef SPH_WITH_GLUT
 void startVisualization(Simulator *simulator);  // display.cpp of the caller
 #endif
 
-static void usage() {
-    printf("Program Options:\n");
-    printf("  -n  <NUM_PARTICLES>    Number of particles to simulate\n");
-    printf("  -i  <random/grid>      Initialization mode: random or grid\n");
-    printf("  -m  <free/time>        Execution mode: free or timed\n");
-    printf("  -b  <BOX_DIM>          (extension) box edge length, default 10\n");
-    printf("  -c  <CELLS_PER_DIM>    (extension) grid cells per dimension, default 100\n");
-    printf("  -k  <flat/morton>      (extension) cell key used by the sort, default flat\n");
-    printf("  -s  <STEPS>            (extension) timed iterations, default 100\n");
-    printf("  -?                     This message\n");
+namespace {
+
+struct Options {
+    int particles = 1000;       // ref: main.cpp:21
+    bool random = false;        // ref: main.cpp:22 (grid)
+    bool timed = true;          // ref: main.cpp:23 (time)
+    float box = 10.f;           // ref: main.cpp:63
+    float cells = 100.f;        // ref: main.cpp:63
+    int steps = 100;            // ref: main.cpp:69
+    int frames = 600;
+    std::string load, dump;
+};
+
+void usage() {
+    static const char *lines[] = {
+        "Program Options:",
+        "  -n  <NUM_PARTICLES>    Number of particles to simulate",
+        "  -i  <random/grid>      Initialization mode: random or grid",
+        "  -m  <free/time>        Execution mode: free or timed",
+        "  -b  <BOX_DIM>          (extension) box edge length, default 10",
+        "  -c  <CELLS_PER_DIM>    (extension) grid cells per dimension, default 100",
+        "  -k  <flat/morton>      (extension) cell key used by the sort, default flat",
+        "  -s  <STEPS>            (extension) timed iterations, default 100",
+        "  -l/-d <FILE>           (extension) load initial / dump final state",
+        "  -?                     This message",
+    };
+    for (const char *l : lines) printf("%s\n", l);
 }
 
-static bool one_of(const std::string &v, const char *a, const char *b) { return v == a || v == b; }
+// An option that takes one of two words; anything else is the reference's error path
+// (message on stdout, usage, exit status 1 -- ref: main.cpp:31-37, 41-47).
+bool choice(char flag, const std::string &value, const char *yes, const char *no, bool &out) {
+    if (value != yes && value != no) {
+        std::cout << "Invalid argument for option -" << flag << ": " << value << std::endl;
+        usage();
+        return false;
+    }
+    out = (value == yes);
+    return true;
+}
 
-static const char kMagic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', 0};
+// returns -1 to continue, otherwise the exit status
+int parse(int argc, char **argv, Options &o) {
+    for (int c; (c = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:?")) != -1;) {
+        const std::string v = optarg ? optarg : "";
+        bool morton = false;
+        switch (c) {
+        case 'n': o.particles = std::stoi(v); break;
+        case 'i': if (!choice('i', v, "random", "grid", o.random)) return 1; break;
+        case 'm': if (!choice('m', v, "time", "free", o.timed)) return 1; break;
+        case 'k':
+            if (!choice('k', v, "morton", "flat", morton)) return 1;
+            setenv("SPH_KEY_MODE", morton ? "morton" : "flat", 1);
+            break;
+        case 'b': o.box = std::stof(v); break;
+        case 'c': o.cells = (float)std::stoi(v); break;
+        case 's': o.steps = std::stoi(v); break;
+        case 'f': o.frames = std::stoi(v); break;
+        case 'l': o.load = v; break;
+        case 'd': o.dump = v; break;
+        default: usage(); return 1;   // '?' and unknown flags (ref: main.cpp:51-53)
+        }
+    }
+    return -1;
+}
 
-static bool load_state(const std::string &path, int n, std::vector<float> &pos, std::vector<float> &vel) {
+const char kMagic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', 0};
+
+bool load_state(const std::string &path, int n, std::vector<float> &pos, std::vector<float> &vel) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
     char magic[8];
@@ -62,7 +113,7 @@ static bool load_state(const std::string &path, int n, std::vector<float> &pos, 
     return ok;
 }
 
-static bool dump_state(const std::string &path, int n, const std::vector<float> &pos, const std::vector<float> &vel) {
+bool dump_state(const std::string &path, int n, const std::vector<float> &pos, const std::vector<float> &vel) {
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) return false;
     int32_t m = n;
@@ -71,95 +122,35 @@ static bool dump_state(const std::string &path, int n, const std::vector<float> 
     return fclose(f) == 0 && ok;
 }
 
+}  // namespace
+
 int main(int argc, char **argv) {
-    int numParticles = 1000;
-    bool randomInit = false;
-    bool benchmark = true;
-    float boxDim = 10.f;
-    float cells = 100;
-    int numIters = 100;
-    int frames = 600;
-    std::string loadPath, dumpPath;
-    int opt;
+    Options o;
+    const int early = parse(argc, argv, o);
+    if (early >= 0) return early;
 
-    while ((opt = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:?")) != -1) {
-        const std::string arg = optarg ? optarg : "";
-        switch (opt) {
-        case 'n':
-            numParticles = std::stoi(arg);
-            break;
-        case 'i':
-            if (!one_of(arg, "random", "grid")) {
-                std::cout << "Invalid argument for option -i: " << arg << std::endl;
-                usage();
-                return 1;
-            }
-            randomInit = (arg == "random");
-            break;
-        case 'm':
-            if (!one_of(arg, "time", "free")) {
-                std::cout << "Invalid argument for option -m: " << arg << std::endl;
-                usage();
-                return 1;
-            }
-            benchmark = (arg == "time");
-            break;
-        case 'b':
-            boxDim = std::stof(arg);
-            break;
-        case 'c':
-            cells = (float)std::stoi(arg);
-            break;
-        case 'k':
-            if (!one_of(arg, "flat", "morton")) {
-                std::cout << "Invalid argument for option -k: " << arg << std::endl;
-                usage();
-                return 1;
-            }
-            setenv("SPH_KEY_MODE", arg.c_str(), 1);
-            break;
-        case 's':
-            numIters = std::stoi(arg);
-            break;
-        case 'f':
-            frames = std::stoi(arg);
-            break;
-        case 'l':
-            loadPath = arg;
-            break;
-        case 'd':
-            dumpPath = arg;
-            break;
-        case '?':
-            usage();
-            return 1;
-        }
-    }
-
-    // ref: main.cpp:57-63
-    float h = .1f;
-    float h_pow_6 = pow(h, 6);
-    float h_pow_9 = pow(h, 9);
-    float v_kernel_coeff = 45.f / (PI * h_pow_6);
-    float d_kernel_coeff = 315.f / (64.f * PI * h_pow_9);
-    Settings settings = {randomInit,     numParticles, h,     v_kernel_coeff,
-                         d_kernel_coeff, boxDim,       cells, .01};
+    // kernel coefficients exactly as the reference computes them (ref: main.cpp:57-61):
+    // pow(float, int) is the double overload, rounded back to float
+    const float h = .1f;
+    const float h6 = pow(h, 6), h9 = pow(h, 9);
+    Settings settings = {o.random, o.particles, h, 45.f / (PI * h6), 315.f / (64.f * PI * h9),
+                         o.box,    o.cells,     .01};
 
     Simulator *simulator = new Simulator(&settings);
     simulator->setup();
     if (simulator->status() != 0) return 2;  // the reference would carry on silently
-    if (!loadPath.empty()) {
+    if (!o.load.empty()) {
         std::vector<float> pos, vel;
-        if (!load_state(loadPath, numParticles, pos, vel) ||
+        if (!load_state(o.load, o.particles, pos, vel) ||
             sph_set_state(simulator->handle(), pos.data(), vel.data()) != 0) {
-            fprintf(stderr, "sph: cannot load %d particles from %s: %s\n", numParticles, loadPath.c_str(), sph_last_error());
+            fprintf(stderr, "sph: cannot load %d particles from %s: %s\n", o.particles, o.load.c_str(), sph_last_error());
             return 2;
         }
     }
 
-    if (benchmark) {
+    if (o.timed) {
         Times times;
-        for (int i = 0; i < numIters; i++) {
+        for (int i = 0; i < o.steps; i++) {
             simulator->simulateAndTime(&times);
             if (simulator->status() != 0) return 2;
         }
@@ -169,24 +160,24 @@ int main(int argc, char **argv) {
         glutInit(&argc, argv);
         startVisualization(simulator);
 #else
-        auto t0 = std::chrono::steady_clock::now();
+        const auto t0 = std::chrono::steady_clock::now();
         double checksum = 0.0;
-        for (int f = 0; f < frames; f++) {
+        for (int f = 0; f < o.frames; f++) {
             simulator->simulate();  // what display() does per frame (ref: display.cpp:36-37)
             if (simulator->status() != 0) return 2;
             const float3 *p = simulator->getPosition();
-            checksum += p[f % (numParticles > 0 ? numParticles : 1)].y;
+            checksum += p[f % (o.particles > 0 ? o.particles : 1)].y;
         }
-        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("free mode (headless build, no GLUT): %d frames in %.3f s = %.1f frames/s (checksum %.6f)\n",
-               frames, dt, frames / dt, checksum);
+               o.frames, dt, o.frames / dt, checksum);
 #endif
     }
-    if (!dumpPath.empty()) {
-        std::vector<float> pos((size_t)3 * numParticles), vel((size_t)3 * numParticles);
+    if (!o.dump.empty()) {
+        std::vector<float> pos((size_t)3 * o.particles), vel((size_t)3 * o.particles);
         if (sph_get_state(simulator->handle(), pos.data(), vel.data()) != 0 ||
-            !dump_state(dumpPath, numParticles, pos, vel)) {
-            fprintf(stderr, "sph: cannot dump the state to %s: %s\n", dumpPath.c_str(), sph_last_error());
+            !dump_state(o.dump, o.particles, pos, vel)) {
+            fprintf(stderr, "sph: cannot dump the state to %s: %s\n", o.dump.c_str(), sph_last_error());
             return 2;
         }
     }

@@ -30,7 +30,7 @@ SphOptions options_from_env() {
 
 }  // namespace
 
-Simulator::Simulator(Settings *settings) : impl(NULL), settings(settings) {}
+Simulator::Simulator(Settings *settings) : settings(settings), impl(NULL) {}
 
 Simulator::~Simulator() {
     sph_destroy(impl);

@@ -2,8 +2,8 @@
 // (ref: src/simulator.h:1-74), backed by the B200-native library libsph_b200.so.
 //
 // A caller written against the reference -- src/main.cpp (time mode) and
-// src/display.cpp (free mode) -- compiles against this header unchanged: same
-// macros, same positional `Settings` aggregate, same `class Simulator` members with
+// src/display.cpp (free mode) -- compiles against this header unchanged: same constant
+// names, same positional `Settings` aggregate, same `class Simulator` members with
 // the same meaning:
 //
 //   Simulator(Settings*)   records the pointer only; the caller keeps ownership and the
@@ -23,50 +23,44 @@
 // float4 arrays on the device instead.
 #pragma once
 
+#include <cuda_runtime.h>  // float3, int2 (the reference header pulls them in the same way)
 #include <stdio.h>
 
-#include "cuda_runtime.h"  // float3, int2 (as in the reference header)
 #include "times.h"
 
-// Physics constants (ref: simulator.h:6-12).  The device code keeps its own copies
-// in csrc/sph_common.cuh; these exist because callers use PI (main.cpp:60-61).
-#define PI 3.14159265f
-#define MASS 0.02f
-#define GAS_CONSTANT 1.f
-#define REST_DENSITY 1000.f
-#define VISCOSITY 1.f
-#define GRAVITY -9.8f
-#define ELASTICITY 0.5f
+// Physics constants under the reference's names (ref: simulator.h:6-12; typed constants
+// instead of macros -- callers only use them in expressions, e.g. main.cpp:60-61).  The
+// device code keeps its own copies in csrc/sph_common.cuh.
+constexpr float PI = 3.14159265f;
+constexpr float MASS = 0.02f;
+constexpr float REST_DENSITY = 1000.f;
+constexpr float GAS_CONSTANT = 1.f;
+constexpr float VISCOSITY = 1.f;
+constexpr float GRAVITY = -9.8f;
+constexpr float ELASTICITY = 0.5f;
 
-// Window rectangle that maps onto the box for mouse pushes (ref: simulator.h:14-17,
-// used by display.cpp:24-25).
-#define BOX_MAX_X (600)
-#define BOX_MIN_X (200)
-#define BOX_MAX_Y (450)
-#define BOX_MIN_Y (150)
+// Window rectangle, in pixels, that maps onto the box for mouse pushes
+// (ref: simulator.h:14-17, used by display.cpp:24-25).
+constexpr int BOX_MIN_X = 200, BOX_MAX_X = 600;
+constexpr int BOX_MIN_Y = 150, BOX_MAX_Y = 450;
 
 // Field order and types are the reference's (ref: simulator.h:19-31): callers
 // aggregate-initialise it positionally (main.cpp:62-63).  numCellsPerDim really is a
 // float there.  sizeof == 32; include/sph_b200.h's SphSettings has the same layout.
 struct Settings {
-    bool randomInit;
-    int numParticles;
-    float h;
-
-    float v_kernel_coeff;  // 45 / (pi h^6)
-    float d_kernel_coeff;  // 315 / (64 pi h^9)
-
-    float boxDim;
-    float numCellsPerDim;
+    bool randomInit;        // -i random | grid
+    int numParticles;       // -n
+    float h;                // smoothing length == cell edge
+    float v_kernel_coeff;   // 45 / (pi h^6)
+    float d_kernel_coeff;   // 315 / (64 pi h^9)
+    float boxDim;           // box edge
+    float numCellsPerDim;   // boxDim / h
     float timestep;
 };
 
-struct sph_sim;  // opaque handle of the C ABI
+struct sph_sim;  // opaque handle of the C ABI (include/sph_b200.h)
 
 class Simulator {
-  private:
-    sph_sim *impl;
-
   public:
     const Settings *settings;
 
@@ -74,9 +68,7 @@ class Simulator {
     virtual ~Simulator();
 
     void setup();
-
     const float3 *getPosition();
-
     void simulate();
     void simulateAndTime(Times *times);
     void moveParticles(int2 mouse_pos);
@@ -89,6 +81,7 @@ class Simulator {
     sph_sim *handle() const { return impl; }
 
   private:
+    sph_sim *impl;
     int lastStatus = 0;
     void note(int rc, const char *what);
 };
