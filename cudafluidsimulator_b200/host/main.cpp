@@ -9,6 +9,9 @@
 //   -k <flat|morton>                cell-key form of the sort
 //   -s <steps>                      iterations in time mode (default 100, main.cpp:69)
 //   -f <frames>                     frames to run in headless free mode (default 600)
+//   -o <prefix>                     headless free mode: write every frame as <prefix>_NNNN.ppm (the box
+//                                   outline in white, particles as blue points, x right / y up -- the
+//                                   headless stand-in for display.cpp's GL_POINTS view)
 //   -l <file> / -d <file>           load the initial state from / dump the final state to a file
 //                                   (state I/O; the reference has none).  Format: "SPHB200\0",
 //                                   int32 N, N x 3 float32 positions, N x 3 float32 velocities
@@ -42,7 +45,7 @@ struct Options {
     float cells = 100.f;        // ref: main.cpp:63
     int steps = 100;            // ref: main.cpp:69
     int frames = 600;
-    std::string load, dump;
+    std::string load, dump, frames_prefix;
 };
 
 void usage() {
@@ -56,6 +59,7 @@ void usage() {
         "  -k  <flat/morton>      (extension) cell key used by the sort, default flat",
         "  -s  <STEPS>            (extension) timed iterations, default 100",
         "  -l/-d <FILE>           (extension) load initial / dump final state",
+        "  -f/-o <N>/<PREFIX>     (extension) headless free mode: frames to run / PPM frame prefix",
         "  -?                     This message",
     };
     for (const char *l : lines) printf("%s\n", l);
@@ -75,7 +79,7 @@ bool choice(char flag, const std::string &value, const char *yes, const char *no
 
 // returns -1 to continue, otherwise the exit status
 int parse(int argc, char **argv, Options &o) {
-    for (int c; (c = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:?")) != -1;) {
+    for (int c; (c = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:o:?")) != -1;) {
         const std::string v = optarg ? optarg : "";
         bool morton = false;
         switch (c) {
@@ -92,6 +96,7 @@ int parse(int argc, char **argv, Options &o) {
         case 'f': o.frames = std::stoi(v); break;
         case 'l': o.load = v; break;
         case 'd': o.dump = v; break;
+        case 'o': o.frames_prefix = v; break;
         default: usage(); return 1;   // '?' and unknown flags (ref: main.cpp:51-53)
         }
     }
@@ -119,6 +124,32 @@ bool dump_state(const std::string &path, int n, const std::vector<float> &pos, c
     int32_t m = n;
     bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(&m, 4, 1, f) == 1 &&
               fwrite(pos.data(), 4, pos.size(), f) == pos.size() && fwrite(vel.data(), 4, vel.size(), f) == vel.size();
+    return fclose(f) == 0 && ok;
+}
+
+// One frame as a binary PPM: orthographic view along -z (x right, y up), box outline white,
+// particles blue -- what display.cpp draws with GL_LINES / GL_POINTS, minus the perspective.
+bool write_frame(const std::string &prefix, int frame, const float3 *p, int n, float box) {
+    const int W = 480, H = 480, margin = 20;
+    std::vector<unsigned char> img((size_t)W * H * 3, 0);
+    const float scale = (W - 2 * margin) / box;
+    auto put = [&](int x, int y, unsigned char r, unsigned char g, unsigned char b) {
+        if (x < 0 || x >= W || y < 0 || y >= H) return;
+        unsigned char *q = &img[((size_t)(H - 1 - y) * W + x) * 3];
+        q[0] = r; q[1] = g; q[2] = b;
+    };
+    for (int t = 0; t <= W - 2 * margin; ++t) {
+        put(margin + t, margin, 255, 255, 255); put(margin + t, H - margin, 255, 255, 255);
+        put(margin, margin + t, 255, 255, 255); put(W - margin, margin + t, 255, 255, 255);
+    }
+    for (int i = 0; i < n; ++i)
+        put(margin + (int)(p[i].x * scale), margin + (int)(p[i].y * scale), 40, 90, 255);
+    char name[512];
+    snprintf(name, sizeof name, "%s_%04d.ppm", prefix.c_str(), frame);
+    FILE *f = fopen(name, "wb");
+    if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", W, H);
+    const bool ok = fwrite(img.data(), 1, img.size(), f) == img.size();
     return fclose(f) == 0 && ok;
 }
 
@@ -167,6 +198,10 @@ int main(int argc, char **argv) {
             if (simulator->status() != 0) return 2;
             const float3 *p = simulator->getPosition();
             checksum += p[f % (o.particles > 0 ? o.particles : 1)].y;
+            if (!o.frames_prefix.empty() && !write_frame(o.frames_prefix, f, p, o.particles, o.box)) {
+                fprintf(stderr, "sph: cannot write frame %d to %s_*.ppm\n", f, o.frames_prefix.c_str());
+                return 2;
+            }
         }
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("free mode (headless build, no GLUT): %d frames in %.3f s = %.1f frames/s (checksum %.6f)\n",

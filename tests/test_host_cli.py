@@ -101,3 +101,13 @@ def test_state_dump_and_load_round_trip(tmp_path):
     pb, pc = fb[12:].view(np.float32), fc[12:].view(np.float32)
     np.testing.assert_allclose(pb, pc, rtol=1e-5, atol=1e-5)
     assert run("-n", "4000", "-l", str(a)).returncode == 2     # particle count mismatch is an error
+
+
+@pytest.mark.gpu
+def test_headless_free_mode_writes_frames(tmp_path):
+    prefix = tmp_path / "frame"
+    r = run("-n", "20000", "-m", "free", "-f", "3", "-o", str(prefix))
+    assert r.returncode == 0 and "3 frames" in r.stdout, r.stderr
+    data = (tmp_path / "frame_0002.ppm").read_bytes()
+    assert data.startswith(b"P6\n480 480\n255\n") and len(data) == 15 + 480 * 480 * 3
+    assert data.count(bytes([40, 90, 255])) > 50      # particles were drawn
