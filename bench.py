@@ -447,8 +447,16 @@ def run_ours(args, wl, rank, local_rank, world):
         "reorder_cellstart": 8 + 32 + 32 + 12 + 4 * (wl["numCellsPerDim"] ** 3) / n,
         "density": 16 + 12 + 8, "force_integrate": 16 + 16 + 8 + 4 + 8 + 16 + 16 + 4 + 12,
     }
-    ncu_kernel = {"density": "k_density_flat<0, 1>", "force_integrate": "k_force_integrate_flat",
+    ncu_kernel = {"density": "k_density_flat<0", "force_integrate": "k_force_integrate_flat",
                   "reorder_cellstart": "k_reorder", "sort_passes": "k_onesweep<0>", "histogram": "k_histogram"}
+
+    def kernel_traffic(stage):   # DRAM bytes per launch of that stage's kernel from the committed ncu capture
+        if not traffic or stage not in ncu_kernel:
+            return None
+        for name, b in traffic["bytes_per_launch"].items():
+            if name.startswith(ncu_kernel[stage]):
+                return b
+        return None
     traffic = None
     tfile = ROOT / "profiles" / "r01_traffic.json"
     if tfile.exists() and args.workload == "16m_grid":
@@ -471,7 +479,7 @@ def run_ours(args, wl, rank, local_rank, world):
     if dom in flops_stage:
         roof = {"kernel": dom, "bound": "fp32", "achieved": d["algorithmic_TFLOPs"], "peak": round(fp32_peak_tflops, 2),
                 "unit": "TFLOP/s", "frac": d["fp32_frac"],
-                "traffic": (traffic["bytes_per_launch"].get(ncu_kernel.get(dom)) if traffic else None),
+                "traffic": kernel_traffic(dom),
                 "traffic_source": traffic["source"] if traffic else None,
                 "algorithmic_bytes_per_launch": bytes_stage[dom] * n,
                 "peak_source": f"SMs*128 lanes*2*clocks.max.sm ({sm_count} SMs, {sm_max_mhz:.0f} MHz from "
@@ -482,7 +490,7 @@ def run_ours(args, wl, rank, local_rank, world):
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": d["hbm_frac"],
-                "traffic": (traffic["bytes_per_launch"].get(ncu_kernel.get(dom)) if traffic else None),
+                "traffic": kernel_traffic(dom),
                 "traffic_source": traffic["source"] if traffic else None,
                 "algorithmic_bytes_per_launch": bytes_stage[dom] * n,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})"}
