@@ -46,8 +46,8 @@ class SphOptions(C.Structure):
         ("z_cell_lo", C.c_int32), ("z_cell_hi", C.c_int32),
         ("no_mask_handoff", C.c_int32),
         ("nz_cells", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32),
-        ("pipeline_readback", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("pipeline_readback", C.c_int32), ("stage_tiles", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 

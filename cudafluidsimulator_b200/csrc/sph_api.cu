@@ -140,6 +140,7 @@ void enqueue_build(sph_sim *s) {
     SortHooks hooks{s, sort_before, sort_after};
     s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], s->p.n, s->passes,
                                      s->d.sort_scratch, s->sm_count, s->stream, &hooks);
+    s->d.sorted_pairs = s->d.pairs[s->sorted_buf];
     stage_begin(s, kStReorder);
     launch_reorder(s->p, s->d, s->sorted_buf, s->p.n, s->sm_count, s->stream);
     stage_end(s);
@@ -516,8 +517,12 @@ int sph_setup(sph_sim *s) {
     CU(cudaMemset(s->p.dbg, 0, sizeof(uint32_t)));
     if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
     if (s->p.key_mode == SPH_KEY_FLAT) {
-        CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2) * sizeof(float4)));
-        CU(cudaMalloc(&d.pair_z, ((scap + 1) / 2) * sizeof(float2)));
+        // + 2 records: the staged tiles copy even-aligned pair ranges
+        CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2 + 2) * sizeof(float4)));
+        CU(cudaMalloc(&d.pair_z, ((scap + 1) / 2 + 2) * sizeof(float2)));
+        CU(cudaMemset(d.pair_xy, 0, ((scap + 1) / 2 + 2) * sizeof(float4)));
+        CU(cudaMemset(d.pair_z, 0, ((scap + 1) / 2 + 2) * sizeof(float2)));
+        d.stage_tiles = s->opt.stage_tiles ? 1 : 0;
     }
     if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
         const size_t ctas = (cap + kBlock - 1) / kBlock;
@@ -917,6 +922,7 @@ int sph_slab_build_async(sph_sim *s) {
                                          s->d.sort_scratch, s->sm_count, s->stream, &hooks);
     }
     p.n = n_live;   // emigrated particles carry dead_key and sit behind the live ones
+    s->d.sorted_pairs = s->d.pairs[s->sorted_buf];
     stage_begin(s, kStReorder);
     launch_reorder(p, s->d, s->sorted_buf, n_sort, s->sm_count, s->stream);
     stage_end(s);

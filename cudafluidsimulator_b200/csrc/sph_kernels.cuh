@@ -23,6 +23,8 @@ struct DeviceState {
     uint32_t *sort_scratch;
     double *stats;               // 2 doubles
     int32_t *counts;             // optional 2*n scratch for K and C
+    const uint64_t *sorted_pairs;  // pairs[sorted buffer] of this step: key of sorted slot i in the high word
+    int stage_tiles;             // 1: dense CTAs run k_density_tile (TMA-staged neighbour tiles)
     uint32_t *nbits;             // in-range bit masks density hands to force; kMaskWords words
                                  // per particle, [CTA][word][lane] interleaved
     // slab mode: particles that left the owned z-layers during integration, per side

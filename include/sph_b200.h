@@ -95,7 +95,10 @@ typedef struct SphOptions {
                              mode; the simulator's internal state runs one step ahead, so the
                              state getters and sph_push() refer to step k+1.  Meant for loops that
                              only call sph_step()/sph_positions_host() (`-m time`-like).       */
-    int32_t reserved[4];
+    int32_t stage_tiles;  /* 1: dense CTAs (128 consecutive particles within a few cells of one
+                             row) compute density out of neighbour tiles staged in shared memory
+                             by bulk TMA (A/B switch; see DESIGN.md 3.4 for the measurement)    */
+    int32_t reserved[3];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */

@@ -25,12 +25,14 @@ ap.add_argument("--workload", default="16m_grid", choices=list(WORKLOADS))
 ap.add_argument("--pre", type=int, default=100)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--key", default="flat")
+ap.add_argument("--stage-tiles", action="store_true", help="SphOptions.stage_tiles (TMA-staged dense CTAs)")
 a = ap.parse_args()
 wl = WORKLOADS[a.workload]
 ctypes.CDLL("libc.so.6").srand(1)
 sim = sph.Simulator(sph.Settings(numParticles=wl["n"], randomInit=wl["randomInit"], boxDim=wl["boxDim"],
                                  numCellsPerDim=wl["numCellsPerDim"]),
-                    key_mode=sph.SPH_KEY_MORTON if a.key == "morton" else sph.SPH_KEY_FLAT)
+                    key_mode=sph.SPH_KEY_MORTON if a.key == "morton" else sph.SPH_KEY_FLAT,
+                    stage_tiles=a.stage_tiles)
 sim.setup()
 sim.advance(a.pre)
 K, C = sim.get_neighbor_counts()

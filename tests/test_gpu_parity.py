@@ -293,6 +293,30 @@ def test_mask_handoff_is_bitwise_neutral():
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("per_cell", [30.0, 80.0, 400.0])
+def test_tma_staged_tiles_are_bitwise_neutral(per_cell):
+    """SphOptions.stage_tiles: dense CTAs take their candidates from shared-memory tiles filled
+    by bulk TMA.  Same candidates in the same order => bit-identical density, force and state.
+    per_cell 400 overflows the tile capacity for some CTAs (global-memory fallback in the tile
+    kernel); the halo keeps non-qualifying CTAs in the same launch."""
+    pos, vel = compressed_state(40000, seed=29, per_cell=per_cell)
+    rng = np.random.default_rng(30)
+    halo = rng.uniform(1.0, 9.0, size=(20000, 3)).astype(np.float32)
+    pos = np.concatenate([pos, halo]); vel = np.concatenate([vel, np.zeros_like(halo)])
+    out = []
+    for staged in (False, True):
+        sim = sph.Simulator(sph.Settings(numParticles=len(pos)), record_force=True, stage_tiles=staged)
+        sim.setup()
+        sim.set_state(pos, vel)
+        sim.simulate()
+        rho, prs, f = sim.get_density_pressure_force()
+        sim.advance(4)
+        out.append((rho, prs, f) + sim.get_state())
+        sim.close()
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_pipelined_readback_hands_out_identical_positions():
     """SphOptions.pipeline_readback overlaps the D2H of step k with the computation of step
     k+1; every sph_step() must still return exactly the positions of the blocking mode."""
