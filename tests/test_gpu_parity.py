@@ -270,6 +270,45 @@ def test_full_size_properties(n, init):
     sim.close()
 
 
+def test_16m_developed_subdomain_matches_oracle():
+    """BASELINE config 3 at its full size (16 M particles, 256^3 cells), developed for 60 steps so
+    the floor pile-up exists.  The oracle cannot run 16 M, but interactions reach only h: a
+    sub-domain plus a 2.5 h halo of the SAME state is a closed problem for the particles inside,
+    so their candidate / neighbour counts must match bit-exactly and density, force and the
+    next position within the single-step tolerances (order inside a cell follows the sort
+    history here and the id order in the sub-problem, hence no bit-exact density)."""
+    n = 16_000_000
+    sim = make(n, boxDim=25.6, numCellsPerDim=256.0)
+    sim.advance(60)
+    pos, vel = sim.get_state()
+    K, Cn = sim.get_neighbor_counts()
+    sim.simulate()
+    rho, prs, f = sim.get_density_pressure_force()   # of the state (pos, vel)
+    p1, _ = sim.get_state()
+    sim.close()
+
+    lo = np.float32([8.0, 0.0, 12.0]); hi = np.float32([10.0, 1.2, 14.0])
+    halo = np.float32(0.25)
+    sub = np.flatnonzero(np.all((pos >= lo - halo) & (pos < hi + halo), axis=1))   # ascending id
+    inner = np.all((pos[sub] >= lo) & (pos[sub] < hi), axis=1)
+    assert inner.sum() > 5000 and len(sub) < 400_000
+    o = CpuOracle(len(sub), boxDim=25.6, numCellsPerDim=256)
+    o.set_state(pos[sub], vel[sub])
+    orho, oprs, oK, oC = o.density()
+    np.testing.assert_array_equal(K[sub][inner], oK[inner])
+    np.testing.assert_array_equal(Cn[sub][inner], oC[inner])
+    assert oK[inner].max() > 60                      # the dense regime is in the sample
+    np.testing.assert_allclose(rho[sub][inner], orho[inner], rtol=2e-6, atol=0)
+    np.testing.assert_allclose(prs[sub][inner], oprs[inner], rtol=0, atol=2e-6 * float(orho.max()))
+    # forces from the full-domain density of the same particles (ours), oracle arithmetic
+    of = o.forces(pos[sub], vel[sub], rho[sub], prs[sub])
+    tol = force_tolerance(o, pos[sub], vel[sub], rho[sub], prs[sub], rel=RTOL_F)
+    err = np.abs(f[sub] - of)
+    assert np.all(err[inner] <= tol[inner]), f"force: worst excess {np.max(err[inner] / tol[inner]):.3g}x"
+    o.step()
+    np.testing.assert_allclose(p1[sub][inner], o.pos[inner], rtol=RTOL_POS, atol=2e-6)
+
+
 def test_mask_handoff_is_bitwise_neutral():
     """Dense particles (C > 64) read density's in-range bit masks in the force kernel;
     pair order and arithmetic are unchanged, so results must be bit-identical to the
