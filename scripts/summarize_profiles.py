@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Turns the ncu artefacts a gpurun call brought back (gpurun_out/) into the committed
-summaries under profiles/:   python scripts/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep>"""
+summaries under profiles/:
+  python scripts/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep> [<early-state.ncu-rep>]"""
 import collections
 import csv
 import subprocess
@@ -34,47 +35,60 @@ lines = [f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3 --n
 for k, (c, t) in agg.items():
     lines.append(f"| {k} | {c} | {t:.3f} | {100 * t / tot:.1f} % | {t / c:.4f} |")
 
-# -- full capture: one plainly launched step at the developed state ----------------------
-raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h2, units, d2 = rr[0], rr[1], rr[2:]
-jx = {h: i for i, h in enumerate(h2)}
-want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs/thread"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
-        ("sm__inst_executed.avg.per_cycle_active", "IPC (max ~3.6 measured, 4 nominal)"),
-        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
-        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
-        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
-        ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instr"),
-        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput %"),
-        ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
-        ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"),
-        ("smsp__inst_executed.sum", "warp instructions")]
-names = [r[jx["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "") for r in d2]
-lines += ["", f"# {tag}: ncu --set full --clock-control none, ONE plainly launched step of the 16M grid workload at the",
-          "# state after 100 steps (scripts/profile_step.py --pre 100): mean candidates 116, mean neighbours 25.",
-          "", "| metric | " + " | ".join(names) + " |", "|---|" + "---|" * len(names)]
-for key, label in want:
-    if key in jx:
-        vals = []
-        for r in d2:
-            v = r[jx[key]]
-            try:
-                v = f"{float(v.replace(',', '')):.4g}"
-            except ValueError:
-                pass
-            vals.append(f"{v} {units[jx[key]]}".strip())
-        lines.append(f"| {label} | " + " | ".join(vals) + " |")
-stalls = [h for h in h2 if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
-lines += ["", "Warp stall reasons (warps stalled per issue; > 0.5 only):", "", "| reason | " + " | ".join(names) + " |",
-          "|---|" + "---|" * len(names)]
-for hname in stalls:
-    vals = [float(r[jx[hname]] or 0) for r in d2]
-    if max(vals) > 0.5:
-        short = hname.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")
-        lines.append(f"| {short} | " + " | ".join(f"{v:.2f}" for v in vals) + " |")
+# -- full captures: one plainly launched step ----------------------------------------------
+def full_table(rep, heading):
+    global h2, units, d2, jx, names, lines
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h2, units, d2 = rr[0], rr[1], rr[2:]
+    jx = {h: i for i, h in enumerate(h2)}
+    want = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread", "regs/thread"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+            ("sm__inst_executed.avg.per_cycle_active", "IPC (max ~3.6 measured, 4 nominal)"),
+            ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+            ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+            ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+            ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+            ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instr"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput %"),
+            ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+            ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"),
+            ("smsp__inst_executed.sum", "warp instructions")]
+    names = [r[jx["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "") for r in d2]
+    lines += ["", f"# {tag}: ncu --set full --clock-control none, ONE plainly launched step of the 16M grid workload at the",
+              heading,
+              "", "| metric | " + " | ".join(names) + " |", "|---|" + "---|" * len(names)]
+    for key, label in want:
+        if key in jx:
+            vals = []
+            for r in d2:
+                v = r[jx[key]]
+                try:
+                    v = f"{float(v.replace(',', '')):.4g}"
+                except ValueError:
+                    pass
+                vals.append(f"{v} {units[jx[key]]}".strip())
+            lines.append(f"| {label} | " + " | ".join(vals) + " |")
+    stalls = [h for h in h2 if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+    lines += ["", "Warp stall reasons (warps stalled per issue; > 0.5 only):", "", "| reason | " + " | ".join(names) + " |",
+              "|---|" + "---|" * len(names)]
+    for hname in stalls:
+        vals = [float(r[jx[hname]] or 0) for r in d2]
+        if max(vals) > 0.5:
+            short = hname.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")
+            lines.append(f"| {short} | " + " | ".join(f"{v:.2f}" for v in vals) + " |")
+
+
+if len(sys.argv) > 4:   # the sparse regime first appended after the developed state below
+    early = Path(sys.argv[4])
+else:
+    early = None
+full_table(rep, "# state after 100 steps (scripts/profile_step.py --pre 100): mean candidates 116, mean neighbours 25.")
+dev = (h2, units, d2, jx, names)
+if early is not None:
+    full_table(early, "# state after 3 steps (--pre 3, the undisturbed lattice: the sparse regime): mean candidates 39, mean neighbours 7.")
+h2, units, d2, jx, names = dev   # the traffic file below describes the developed state
 (out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
 
 # per-launch DRAM traffic of every kernel (bench.py reports it as roofline.traffic)
