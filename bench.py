@@ -273,7 +273,7 @@ def run_slabs(args, wl, rank, local_rank, world):
         b = SlabBackend(st, zlo, zhi, nz, capacity=int(n * 1.2) + 4096, device=local_rank,
                         ghost_capacity=int(n * 0.1) + 4096, emig_capacity=int(n * 0.05) + 4096)
         b.load(my_pos, np.zeros_like(my_pos), my_ids)
-        return b, SlabDriver(b, rank, world)
+        return b, SlabDriver(b, rank, world, overlap=args.overlap)
 
     def barrier():
         dist.barrier()
@@ -587,6 +587,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
     ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: halo exchanges under the interior CTAs instead of after them (A/B switch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

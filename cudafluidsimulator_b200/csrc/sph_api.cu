@@ -996,6 +996,75 @@ int sph_slab_force_async(sph_sim *s) {
     return 0;
 }
 
+// ---- interior / boundary split: lets the caller run the halo exchanges under the interior CTAs ----
+// Particle CTAs [a, b) hold no particle of the lowest / highest owned layer: they need no ghost
+// data (density: positions, force: {p, a}).  Valid after sph_slab_build_finish().
+static void interior_ctas(const sph_sim *s, int *a, int *b) {
+    const uint32_t *c = s->slab_counts_host;   // lo_first, lo_end, hi_first, hi_end (sorted slots)
+    const int lo_end = (int)c[1] - s->p.slot0, hi_first = (int)c[2] - s->p.slot0;
+    *a = std::min((std::max(lo_end, 0) + kBlock - 1) / kBlock, (s->p.n + kBlock - 1) / kBlock);
+    *b = std::max(std::min(hi_first, s->p.n), 0) / kBlock;
+    if (*b < *a) *b = *a;
+}
+
+static Params part_params(const sph_sim *s, int part, int *ctas) {
+    int a, b;
+    interior_ctas(s, &a, &b);
+    Params p = s->p;
+    const int total = (p.n + kBlock - 1) / kBlock;
+    if (part == 0) { p.cta_gap_at = 0; p.cta_gap_len = a; p.cta_count = b - a; }
+    else { p.cta_gap_at = a; p.cta_gap_len = b - a; p.cta_count = total - (b - a); }
+    *ctas = p.cta_count;
+    return p;
+}
+
+int sph_slab_density_part(sph_sim *s, int part, int g_lo, int g_hi) {
+    REQUIRE_SLAB(s);
+    if (part != 0 && part != 1) return fail(SPH_E_INVALID, "part must be 0 (interior) or 1 (boundary)");
+    if (part == 0) {
+        s->p.slot_begin = s->p.slot0;
+        s->p.slot_end = s->p.slot0 + s->p.n;
+    } else {
+        if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
+            return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
+        s->p.slot_begin = s->p.slot0 - g_lo;
+        s->p.slot_end = s->p.slot0 + s->p.n + g_hi;
+        const Params &p = s->p;
+        const uint32_t nn = (uint32_t)p.nc * p.nc;
+        stage_begin(s, kStReorder);
+        launch_ghost_prepare(p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
+        stage_end(s);
+        stage_begin(s, kStReorder);
+        launch_ghost_prepare(p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
+        stage_end(s);
+        s->step_valid = true;
+    }
+    int ctas;
+    const Params p = part_params(s, part, &ctas);
+    if (ctas > 0) {
+        stage_begin(s, kStDensity);
+        launch_density(p, s->th, s->d, false, s->stream);
+        stage_end(s);
+    }
+    return 0;
+}
+
+int sph_slab_force_part(sph_sim *s, int part) {
+    REQUIRE_SLAB(s);
+    if (part != 0 && part != 1) return fail(SPH_E_INVALID, "part must be 0 (interior) or 1 (boundary)");
+    if (part == 0) CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
+    int ctas;
+    const Params p = part_params(s, part, &ctas);
+    if (ctas > 0) {
+        stage_begin(s, kStForce);
+        launch_force_integrate(p, s->th, s->d, s->stream);
+        stage_end(s);
+    }
+    if (part == 1)
+        CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->d.emig_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
 int sph_slab_force_finish(sph_sim *s, SphSlabInfo *info) {
     REQUIRE_SLAB(s);
     if (!info) return fail(SPH_E_INVALID, "null argument");

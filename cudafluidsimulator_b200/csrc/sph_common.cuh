@@ -43,6 +43,10 @@ struct Params {
     int nz;         // global cells along z
     float hi_z;     // global box length along z minus h (z wall)
     uint32_t dead_key;  // slab: key given to emigrated particles; sorts behind every live key
+    // -- launch over a subset of the particle CTAs (slab mode: interior CTAs run while the halo is in
+    //    flight, boundary CTAs afterwards); CTA c of the grid works on particle CTA
+    //    c + (c >= cta_gap_at ? cta_gap_len : 0); cta_count = grid size, 0 = all CTAs
+    int cta_gap_at, cta_gap_len, cta_count;
     // -- self-checking build (-DSPH_BOUNDS_CHECK; compute-sanitizer is closed on the GPU pool)
     int slot_begin, slot_end;   // sorted slots that hold particles this step (ghosts included)
     uint32_t *dbg;              // violation bits are OR-ed in here (see SPH_DBG_* below)
@@ -62,6 +66,12 @@ enum : uint32_t {
 #else
 #define SPH_CHECK(p, cond, bit) do { } while (0)
 #endif
+
+// Particle CTA this thread block works on (see Params::cta_gap_at).
+__device__ __forceinline__ int particle_cta(const Params &p) {
+    const int c = (int)blockIdx.x;
+    return c + (c >= p.cta_gap_at ? p.cta_gap_len : 0);
+}
 
 // ---- cell coordinates and keys ------------------------------------------------
 // ref: simulator.cu:57-76 getGridCell: IEEE divide by h, truncate toward zero.

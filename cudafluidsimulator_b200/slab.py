@@ -141,6 +141,12 @@ class SlabBackend:
     def density(self, g_lo, g_hi):
         self.N.check(self.lib.sph_slab_density(self.h, int(g_lo), int(g_hi)))
 
+    def density_part(self, part, g_lo=0, g_hi=0):
+        self.N.check(self.lib.sph_slab_density_part(self.h, int(part), int(g_lo), int(g_hi)))
+
+    def force_part(self, part):
+        self.N.check(self.lib.sph_slab_force_part(self.h, int(part)))
+
     def force(self):
         i = self.N.SphSlabInfo()
         self.N.check(self.lib.sph_slab_force(self.h, C.byref(i)))
@@ -184,8 +190,11 @@ class SlabBackend:
 class SlabDriver:
     """The per-step exchange protocol between neighbouring slabs (backend-agnostic)."""
 
-    def __init__(self, backend, rank: int, world: int, group=None):
+    def __init__(self, backend, rank: int, world: int, group=None, overlap: bool = False):
         self.b, self.rank, self.world, self.group = backend, rank, world, group
+        # overlap: run the halo exchanges under the interior CTAs (sph_slab_*_part).  Same results;
+        # measured no faster at 16M/GPU (the step is bound by the host-side protocol, DESIGN.md 5.1)
+        self.overlap = overlap
         self.down = rank - 1 if rank > 0 else None          # owner of lower z
         self.up = rank + 1 if rank < world - 1 else None    # owner of higher z
         self.stats = {"ghost_particles": 0, "migrated_particles": 0, "steps": 0}
@@ -199,13 +208,20 @@ class SlabDriver:
         dist.all_gather(out, t, group=self.group)
         return [o.tolist() for o in out]
 
-    def _exchange(self, sends, recvs):
-        """sends / recvs: lists of (tensor, peer); empty tensors are skipped on both sides."""
+    def _exchange_start(self, sends, recvs):
+        """sends / recvs: lists of (tensor, peer); empty tensors are skipped on both sides.
+        Returns the requests; work enqueued before _exchange_wait() overlaps the transfer."""
         ops = [dist.P2POp(dist.irecv, t, peer, group=self.group) for t, peer in recvs if t.numel()]
         ops += [dist.P2POp(dist.isend, t, peer, group=self.group) for t, peer in sends if t.numel()]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def _exchange_wait(reqs):
+        for req in reqs:
+            req.wait()
+
+    def _exchange(self, sends, recvs):
+        self._exchange_wait(self._exchange_start(sends, recvs))
 
     def _neighbour_counts(self, lo, hi):
         """My device counts[lo:hi] -> both neighbours, theirs -> a pinned host mirror
@@ -255,15 +271,29 @@ class SlabDriver:
                     sends.append((a[lo], self.down)); recvs.append((a[glo], self.down))
                 if self.up is not None:
                     sends.append((a[hi], self.up)); recvs.append((a[ghi], self.up))
-            self._exchange(sends, recvs)
+            return self._exchange_start(sends, recvs)
 
-        halo([b.srt_pos, b.srt_vel])          # exchange A
-        b.density(g_lo, g_hi)
-        halo([b.pa])                           # exchange B
+        # interior CTAs (no particle of a boundary layer) need no ghosts: they run under the exchanges
+        split = fast and self.overlap and hasattr(b, "density_part")
+        reqs = halo([b.srt_pos, b.srt_vel])   # exchange A
+        if split:
+            b.density_part(0)
+        self._exchange_wait(reqs)
+        if split:
+            b.density_part(1, g_lo, g_hi)
+        else:
+            b.density(g_lo, g_hi)
+        reqs = halo([b.pa])                    # exchange B
+        if split:
+            b.force_part(0)
+        self._exchange_wait(reqs)
 
         # migration: my emigrants -> neighbours; theirs are appended behind my particles
         if fast:
-            b.force_async()
+            if split:
+                b.force_part(1)
+            else:
+                b.force_async()
             self._neighbour_counts(4, 6)
             f = b.force_finish()
             nb = self._nb_host
@@ -310,8 +340,9 @@ class LocalSlabCluster:
     on different GPUs).  Used to test slab mode on a single GPU and as the one-process /
     many-devices mode."""
 
-    def __init__(self, backends):
+    def __init__(self, backends, split: bool = False):
         self.b = list(backends)
+        self.split = split   # interior / boundary parts, in the order SlabDriver issues them
         self.stats = {"ghost_particles": 0, "migrated_particles": 0, "steps": 0}
 
     def step(self):
@@ -332,12 +363,24 @@ class LocalSlabCluster:
                     dst[i.slot0 + i.n_owned:i.slot0 + i.n_owned + g_hi[r]].copy_(
                         src[j.lo_first:j.lo_first + j.lo_count])
 
+        if self.split:
+            for r in range(W):
+                B[r].density_part(0)
         halo("srt_pos")
         halo("srt_vel")
         for r in range(W):
-            B[r].density(g_lo[r], g_hi[r])
+            if self.split:
+                B[r].density_part(1, g_lo[r], g_hi[r])
+                B[r].force_part(0)
+            else:
+                B[r].density(g_lo[r], g_hi[r])
         halo("pa")
-        f = [b.force() for b in B]
+        if self.split:
+            for b in B:
+                b.force_part(1)
+            f = [b.force_finish() for b in B]
+        else:
+            f = [b.force() for b in B]
         for r in range(W):
             at, n_in = f[r].n_total, 0
             for src_rank, side, cnt in ((r - 1, 1, f[r - 1].emig_up if r > 0 else 0),

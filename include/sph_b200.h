@@ -208,6 +208,17 @@ int sph_slab_force_async(sph_sim *sim);
 int sph_slab_force_finish(sph_sim *sim, SphSlabInfo *info);
 int sph_slab_density(sph_sim *sim, int ghost_lo_count, int ghost_hi_count);
 int sph_slab_force(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
+/* The same two stages in two parts each, so that the exchanges run under compute:
+ *   part 0 = interior: the particle CTAs that hold no particle of the lowest / highest owned
+ *            layer; they read no ghost data, so they may run while exchange A (density) or
+ *            exchange B (force) is in flight.  Valid after sph_slab_build_finish().
+ *   part 1 = boundary: the remaining CTAs, after the exchange completed (density: also builds
+ *            the ghosts' cell ranges; force: also publishes the emigrant counts, i.e. it is
+ *            followed by sph_slab_force_finish()).
+ * Order per step: density 0, [A done], density 1, force 0, [B done], force 1.  Results are
+ * identical to sph_slab_density() / sph_slab_force_async(). */
+int sph_slab_density_part(sph_sim *sim, int part, int ghost_lo_count, int ghost_hi_count);
+int sph_slab_force_part(sph_sim *sim, int part);
 int sph_slab_append(sph_sim *sim, int count);
 int sph_slab_buffers(sph_sim *sim, SphSlabBuffers *out);
 /* Owned live particles (after sph_slab_force: the integrated state), any order. */
