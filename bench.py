@@ -273,7 +273,7 @@ def run_slabs(args, wl, rank, local_rank, world):
         b = SlabBackend(st, zlo, zhi, nz, capacity=int(n * 1.2) + 4096, device=local_rank,
                         ghost_capacity=int(n * 0.1) + 4096, emig_capacity=int(n * 0.05) + 4096)
         b.load(my_pos, np.zeros_like(my_pos), my_ids)
-        return b, SlabDriver(b, rank, world, overlap=args.overlap)
+        return b, SlabDriver(b, rank, world, overlap=not args.no_overlap)
 
     def barrier():
         dist.barrier()
@@ -301,6 +301,10 @@ def run_slabs(args, wl, rank, local_rank, world):
     with ClockSampler(local_rank) as clocks:
         ms = timed(drv.step, args.steps)
     launches = b.launch_count - l0
+    if drv.host_ms is not None and rank == 0:   # SPH_SLAB_TRACE=1: host time per protocol phase
+        tot = args.steps + args.warmup
+        print("host ms/step by phase (rank 0): " +
+              ", ".join(f"{k} {v / tot:.3f}" for k, v in drv.host_ms.items()), file=sys.stderr)
     per_rank = [None] * world
     dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": timed.local_ms / args.steps, **drv.last,
                                       **{k: v for k, v in drv.stats.items()}})
@@ -587,8 +591,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
     ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: halo exchanges under the interior CTAs instead of after them (A/B switch)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: halo exchanges and count round trips after, not under, the interior CTAs (A/B switch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()

@@ -98,8 +98,9 @@ SYMBOLS = {
     "sph_slab_force_async": (C.c_int, [_P]),
     "sph_slab_force_finish": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
     "sph_slab_density": (C.c_int, [_P, C.c_int, C.c_int]),
-    "sph_slab_density_part": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
-    "sph_slab_force_part": (C.c_int, [_P, C.c_int]),
+    "sph_slab_interior_ctas": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sph_slab_density_part": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "sph_slab_force_part": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "sph_slab_force": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
     "sph_slab_append": (C.c_int, [_P, C.c_int]),
     "sph_slab_buffers": (C.c_int, [_P, C.POINTER(SphSlabBuffers)]),

@@ -85,6 +85,7 @@ struct sph_sim {
     bool spec_inflight = false;            // a step is enqueued whose positions were not handed out yet
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_build = nullptr;   // slab mode: the counts of sph_slab_build_async() reached the host
     bool profiling = false;
     std::vector<EventPair> events;
     size_t events_used = 0;
@@ -269,6 +270,7 @@ int free_device(sph_sim *s) {
     cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(s->out_buf[0]); cudaFree(s->out_buf[1]);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_step) cudaEventDestroy(s->ev_step);
+    if (s->ev_build) cudaEventDestroy(s->ev_build);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits); cudaFree(d.pair_xy); cudaFree(d.pair_z);
     memset(&d, 0, sizeof(d));
@@ -932,6 +934,8 @@ int sph_slab_build_async(sph_sim *s) {
     for (int i = 0; i < 4; ++i)
         CU(cudaMemcpyAsync(s->slab_counts + i, cs + at[i], 4, cudaMemcpyDeviceToDevice, s->stream));
     CU(cudaMemcpyAsync(s->slab_counts_host, s->slab_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (!s->ev_build) CU(cudaEventCreateWithFlags(&s->ev_build, cudaEventDisableTiming));
+    CU(cudaEventRecord(s->ev_build, s->stream));
     s->pending_n_sort = n_sort;
     s->pending_n_live = n_live;
     return 0;
@@ -941,8 +945,14 @@ int sph_slab_build_finish(sph_sim *s, SphSlabInfo *info) {
     REQUIRE_SLAB(s);
     if (!info) return fail(SPH_E_INVALID, "null argument");
     memset(info, 0, sizeof(*info));
-    int rc = sync_stream(s);
-    if (rc) return rc;
+    // waits for the build only: work the caller enqueued behind it (a speculative interior density
+    // launch, sph_slab_density_part) keeps the GPU busy across this host round trip
+    if (s->profiling || !s->ev_build) {
+        int rc = sync_stream(s);
+        if (rc) return rc;
+    } else {
+        CU(cudaEventSynchronize(s->ev_build));
+    }
     const uint32_t *b = s->slab_counts_host;
     const int n_live = s->pending_n_live;
     s->n_total = n_live; s->n_dead = 0; s->hashed_upto = n_live;
@@ -1007,41 +1017,51 @@ static void interior_ctas(const sph_sim *s, int *a, int *b) {
     if (*b < *a) *b = *a;
 }
 
-static Params part_params(const sph_sim *s, int part, int *ctas) {
-    int a, b;
-    interior_ctas(s, &a, &b);
-    Params p = s->p;
-    const int total = (p.n + kBlock - 1) / kBlock;
-    if (part == 0) { p.cta_gap_at = 0; p.cta_gap_len = a; p.cta_count = b - a; }
-    else { p.cta_gap_at = a; p.cta_gap_len = b - a; p.cta_count = total - (b - a); }
-    *ctas = p.cta_count;
-    return p;
+int sph_slab_interior_ctas(sph_sim *s, int *cta_a, int *cta_b) {
+    REQUIRE_SLAB(s);
+    if (!cta_a || !cta_b) return fail(SPH_E_INVALID, "null argument");
+    interior_ctas(s, cta_a, cta_b);
+    return 0;
 }
 
-int sph_slab_density_part(sph_sim *s, int part, int g_lo, int g_hi) {
+static int part_params(sph_sim *s, int part, int a, int b, Params *out) {
+    Params p = s->p;
+    const int total = (p.n + kBlock - 1) / kBlock;
+    if ((part != 0 && part != 1) || a < 0 || b < a)
+        return fail(SPH_E_INVALID, "part %d of particle CTAs [%d, %d) is not valid", part, a, b);
+    // a range guessed before the particle count was known may reach past the end: both parts clamp
+    // it the same way (the caller compares its guess with sph_slab_interior_ctas() anyway)
+    a = std::min(a, total);
+    b = std::min(b, total);
+    if (part == 0) { p.cta_gap_at = 0; p.cta_gap_len = a; p.cta_count = b - a; }
+    else { p.cta_gap_at = a; p.cta_gap_len = b - a; p.cta_count = total - (b - a); }
+    *out = p;
+    return 0;
+}
+
+int sph_slab_density_part(sph_sim *s, int part, int cta_a, int cta_b, int g_lo, int g_hi) {
     REQUIRE_SLAB(s);
-    if (part != 0 && part != 1) return fail(SPH_E_INVALID, "part must be 0 (interior) or 1 (boundary)");
+    Params p;
+    int rc = part_params(s, part, cta_a, cta_b, &p);
+    if (rc) return rc;
     if (part == 0) {
-        s->p.slot_begin = s->p.slot0;
-        s->p.slot_end = s->p.slot0 + s->p.n;
+        p.slot_begin = p.slot0;
+        p.slot_end = p.slot0 + p.n;
     } else {
         if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
             return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
-        s->p.slot_begin = s->p.slot0 - g_lo;
-        s->p.slot_end = s->p.slot0 + s->p.n + g_hi;
-        const Params &p = s->p;
+        s->p.slot_begin = p.slot_begin = p.slot0 - g_lo;
+        s->p.slot_end = p.slot_end = p.slot0 + p.n + g_hi;
         const uint32_t nn = (uint32_t)p.nc * p.nc;
         stage_begin(s, kStReorder);
-        launch_ghost_prepare(p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
+        launch_ghost_prepare(s->p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
         stage_end(s);
         stage_begin(s, kStReorder);
-        launch_ghost_prepare(p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
+        launch_ghost_prepare(s->p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
         stage_end(s);
         s->step_valid = true;
     }
-    int ctas;
-    const Params p = part_params(s, part, &ctas);
-    if (ctas > 0) {
+    if (p.cta_count > 0) {
         stage_begin(s, kStDensity);
         launch_density(p, s->th, s->d, false, s->stream);
         stage_end(s);
@@ -1049,13 +1069,13 @@ int sph_slab_density_part(sph_sim *s, int part, int g_lo, int g_hi) {
     return 0;
 }
 
-int sph_slab_force_part(sph_sim *s, int part) {
+int sph_slab_force_part(sph_sim *s, int part, int cta_a, int cta_b) {
     REQUIRE_SLAB(s);
-    if (part != 0 && part != 1) return fail(SPH_E_INVALID, "part must be 0 (interior) or 1 (boundary)");
+    Params p;
+    int rc = part_params(s, part, cta_a, cta_b, &p);
+    if (rc) return rc;
     if (part == 0) CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
-    int ctas;
-    const Params p = part_params(s, part, &ctas);
-    if (ctas > 0) {
+    if (p.cta_count > 0) {
         stage_begin(s, kStForce);
         launch_force_integrate(p, s->th, s->d, s->stream);
         stage_end(s);

@@ -22,6 +22,8 @@ There is no reference equivalent (the reference is single-GPU).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -141,11 +143,17 @@ class SlabBackend:
     def density(self, g_lo, g_hi):
         self.N.check(self.lib.sph_slab_density(self.h, int(g_lo), int(g_hi)))
 
-    def density_part(self, part, g_lo=0, g_hi=0):
-        self.N.check(self.lib.sph_slab_density_part(self.h, int(part), int(g_lo), int(g_hi)))
+    def interior_ctas(self):
+        a, b = C.c_int(), C.c_int()
+        self.N.check(self.lib.sph_slab_interior_ctas(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
-    def force_part(self, part):
-        self.N.check(self.lib.sph_slab_force_part(self.h, int(part)))
+    def density_part(self, part, ctas, g_lo=0, g_hi=0):
+        self.N.check(self.lib.sph_slab_density_part(self.h, int(part), int(ctas[0]), int(ctas[1]),
+                                                    int(g_lo), int(g_hi)))
+
+    def force_part(self, part, ctas):
+        self.N.check(self.lib.sph_slab_force_part(self.h, int(part), int(ctas[0]), int(ctas[1])))
 
     def force(self):
         i = self.N.SphSlabInfo()
@@ -190,14 +198,29 @@ class SlabBackend:
 class SlabDriver:
     """The per-step exchange protocol between neighbouring slabs (backend-agnostic)."""
 
-    def __init__(self, backend, rank: int, world: int, group=None, overlap: bool = False):
+    def __init__(self, backend, rank: int, world: int, group=None, overlap: bool = True):
         self.b, self.rank, self.world, self.group = backend, rank, world, group
-        # overlap: run the halo exchanges under the interior CTAs (sph_slab_*_part).  Same results;
-        # measured no faster at 16M/GPU (the step is bound by the host-side protocol, DESIGN.md 5.1)
+        # overlap: the interior CTAs (sph_slab_*_part) run under the halo exchanges, and the interior
+        # density is launched on a guess from the previous step before the counts of this step have
+        # crossed the host (checked afterwards, redone if wrong).  Same results (DESIGN.md 5.1).
         self.overlap = overlap
+        # host-side time per protocol phase (ms, accumulated) when SPH_SLAB_TRACE=1: shows where the
+        # host, not the GPU, paces the step
+        self.host_ms = {} if os.environ.get("SPH_SLAB_TRACE") else None
+        self._t0 = 0.0
+        self._guess = None        # (cta_a, cta_b) expected to be interior in the next step
+        self.guess_margin = 8     # particle CTAs (1024 particles) the boundary layers may grow per step
         self.down = rank - 1 if rank > 0 else None          # owner of lower z
         self.up = rank + 1 if rank < world - 1 else None    # owner of higher z
         self.stats = {"ghost_particles": 0, "migrated_particles": 0, "steps": 0}
+
+    def _mark(self, name=None):
+        if self.host_ms is None:
+            return
+        now = time.perf_counter()
+        if name is not None:
+            self.host_ms[name] = self.host_ms.get(name, 0.0) + (now - self._t0) * 1e3
+        self._t0 = now
 
     # -- plumbing -------------------------------------------------------------------
     def _counts(self, mine):
@@ -244,10 +267,22 @@ class SlabDriver:
     def step(self):
         b = self.b
         fast = hasattr(b, "build_async")   # device-side counts: neighbours only, one sync per phase
+        self._mark()
+        split = fast and self.overlap and hasattr(b, "density_part")
+        spec = None   # interior CTAs guessed from the previous step, launched before the counts are known
         if fast:
             b.build_async()
+            self._mark("build issue")
             self._neighbour_counts(0, 4)
+            counts_ready = torch.cuda.Event()
+            counts_ready.record()
+            if split and self._guess is not None and self._guess[1] > self._guess[0]:
+                spec = self._guess
+                b.density_part(0, spec)   # keeps the GPU busy across the host round trip below
+            self._mark("count exchange 1 issue")
+            counts_ready.synchronize()
             info = b.build_finish()
+            self._mark("sync 1 (build + counts)")
             nb = self._nb_host
             g_lo = int(nb[0, 3] - nb[0, 2]) if self.down is not None else 0   # their highest layer
             g_hi = int(nb[1, 1] - nb[1, 0]) if self.up is not None else 0     # their lowest layer
@@ -274,28 +309,46 @@ class SlabDriver:
             return self._exchange_start(sends, recvs)
 
         # interior CTAs (no particle of a boundary layer) need no ghosts: they run under the exchanges
-        split = fast and self.overlap and hasattr(b, "density_part")
+        ctas = None
+        if split:
+            ctas = b.interior_ctas()
+            total = (n + 127) // 128
+            if spec is not None and spec[0] >= ctas[0] and spec[1] <= ctas[1] and spec[1] <= total:
+                ctas = spec                       # the guess holds: its density is already running
+            else:
+                spec = None                       # no / wrong guess: launch the true interior now
+            self.stats["speculative_hits"] = self.stats.get("speculative_hits", 0) + (spec is not None)
+            # next step's guess: this step's interior shrunk by a margin on both sides
+            m = self.guess_margin
+            self._guess = (ctas[0] + m, ctas[1] - m) if ctas[1] - ctas[0] > 2 * m else None
+        self._mark("slices")
         reqs = halo([b.srt_pos, b.srt_vel])   # exchange A
-        if split:
-            b.density_part(0)
+        if split and spec is None:
+            b.density_part(0, ctas)
         self._exchange_wait(reqs)
+        self._mark("exchange A issue")
         if split:
-            b.density_part(1, g_lo, g_hi)
+            b.density_part(1, ctas, g_lo, g_hi)
         else:
             b.density(g_lo, g_hi)
+        self._mark("density issue")
         reqs = halo([b.pa])                    # exchange B
         if split:
-            b.force_part(0)
+            b.force_part(0, ctas)
         self._exchange_wait(reqs)
+        self._mark("exchange B issue")
 
         # migration: my emigrants -> neighbours; theirs are appended behind my particles
         if fast:
             if split:
-                b.force_part(1)
+                b.force_part(1, ctas)
             else:
                 b.force_async()
+            self._mark("force issue")
             self._neighbour_counts(4, 6)
+            self._mark("count exchange 2 issue")
             f = b.force_finish()
+            self._mark("sync 2 (density + force + counts)")
             nb = self._nb_host
             # (senders cap at their emigrant buffer; all slabs are created with the same capacity)
             in_dn = min(int(nb[0, 5]), b.emig_capacity) if self.down is not None else 0   # from below, moving up
@@ -318,6 +371,7 @@ class SlabDriver:
                 recvs.append((dst[at + in_dn:at + in_dn + in_up], self.up))
         self._exchange(sends, recvs)
         b.append(in_dn + in_up)
+        self._mark("migration issue")
         if f.overflow:
             raise RuntimeError(f"rank {self.rank}: slab capacity overflow flags {f.overflow}")
         self.stats["ghost_particles"] += g_lo + g_hi
@@ -363,21 +417,22 @@ class LocalSlabCluster:
                     dst[i.slot0 + i.n_owned:i.slot0 + i.n_owned + g_hi[r]].copy_(
                         src[j.lo_first:j.lo_first + j.lo_count])
 
+        ctas = [b.interior_ctas() for b in B] if self.split else None
         if self.split:
             for r in range(W):
-                B[r].density_part(0)
+                B[r].density_part(0, ctas[r])
         halo("srt_pos")
         halo("srt_vel")
         for r in range(W):
             if self.split:
-                B[r].density_part(1, g_lo[r], g_hi[r])
-                B[r].force_part(0)
+                B[r].density_part(1, ctas[r], g_lo[r], g_hi[r])
+                B[r].force_part(0, ctas[r])
             else:
                 B[r].density(g_lo[r], g_hi[r])
         halo("pa")
         if self.split:
-            for b in B:
-                b.force_part(1)
+            for r in range(W):
+                B[r].force_part(1, ctas[r])
             f = [b.force_finish() for b in B]
         else:
             f = [b.force() for b in B]

@@ -208,17 +208,21 @@ int sph_slab_force_async(sph_sim *sim);
 int sph_slab_force_finish(sph_sim *sim, SphSlabInfo *info);
 int sph_slab_density(sph_sim *sim, int ghost_lo_count, int ghost_hi_count);
 int sph_slab_force(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
-/* The same two stages in two parts each, so that the exchanges run under compute:
- *   part 0 = interior: the particle CTAs that hold no particle of the lowest / highest owned
- *            layer; they read no ghost data, so they may run while exchange A (density) or
- *            exchange B (force) is in flight.  Valid after sph_slab_build_finish().
- *   part 1 = boundary: the remaining CTAs, after the exchange completed (density: also builds
- *            the ghosts' cell ranges; force: also publishes the emigrant counts, i.e. it is
- *            followed by sph_slab_force_finish()).
+/* The same two stages in two parts each, so that exchanges and host round trips run under
+ * compute.  The particle CTAs (128 consecutive sorted particles) [cta_a, cta_b) are the
+ * "interior": they must hold no particle of the lowest / highest owned layer, so they read no
+ * ghost data.  sph_slab_interior_ctas() reports the largest such range (valid after
+ * sph_slab_build_finish()); a caller may also enqueue part 0 with a narrower range guessed from
+ * the previous step right behind sph_slab_build_async() -- sph_slab_build_finish() waits for the
+ * build only -- and check the guess against sph_slab_interior_ctas() afterwards.
+ *   part 0 = interior CTAs; part 1 = all the others, after the exchange completed (density:
+ *   also builds the ghosts' cell ranges; force: also publishes the emigrant counts, i.e. it is
+ *   followed by sph_slab_force_finish()).  Both parts of a stage take the same range.
  * Order per step: density 0, [A done], density 1, force 0, [B done], force 1.  Results are
  * identical to sph_slab_density() / sph_slab_force_async(). */
-int sph_slab_density_part(sph_sim *sim, int part, int ghost_lo_count, int ghost_hi_count);
-int sph_slab_force_part(sph_sim *sim, int part);
+int sph_slab_interior_ctas(sph_sim *sim, int *cta_a, int *cta_b);
+int sph_slab_density_part(sph_sim *sim, int part, int cta_a, int cta_b, int ghost_lo_count, int ghost_hi_count);
+int sph_slab_force_part(sph_sim *sim, int part, int cta_a, int cta_b);
 int sph_slab_append(sph_sim *sim, int count);
 int sph_slab_buffers(sph_sim *sim, SphSlabBuffers *out);
 /* Owned live particles (after sph_slab_force: the integrated state), any order. */
