@@ -55,7 +55,7 @@ struct EventPair {
 struct sph_sim {
     SphSettings settings;
     SphOptions opt;
-    Params p;
+    Params p{};   // zero: no slab, no CTA gap (particle_cta() is the identity)
     Thresholds th;
     DeviceState d;
     int sm_count = 148;
