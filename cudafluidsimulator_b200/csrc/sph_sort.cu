@@ -63,17 +63,33 @@ __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
 // Lanes of the warp holding the same 8-bit digit: eight ballots intersected.  (The
 // MATCH.ANY instruction computes the same thing but at a small fraction of the ballot
 // rate -- measured: the pass ran at IPC 0.9 with its warps parked on the match results.)
+// One bit of the digit: peers &= lanes whose bit equals mine.  Test, vote, select and one 3-input
+// logic op (4 SASS instructions); written in PTX because the compiler turns the C form into
+// shift + and + compare + select + vote + logic (6).
+template <int BIT>
+__device__ __forceinline__ void ballot_step(uint32_t &peers, uint32_t d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, b;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+        "selp.b32 t, 0, 0xffffffff, p;\n\t"   // a lane whose bit is clear matches the complement
+        "xor.b32 b, b, t;\n\t"
+        "and.b32 %0, %0, b;\n\t"
+        "}"
+        : "+r"(peers)
+        : "r"(d), "n"(1u << BIT));
+}
+
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 #if SORT_USE_MATCH_INSTRUCTION
     return __match_any_sync(0xffffffffu, d);
 #endif
     uint32_t peers = 0xffffffffu;
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const bool set = (d >> bit) & 1u;
-        const uint32_t b = __ballot_sync(0xffffffffu, set);
-        peers &= set ? b : ~b;
-    }
+    ballot_step<0>(peers, d); ballot_step<1>(peers, d); ballot_step<2>(peers, d); ballot_step<3>(peers, d);
+    ballot_step<4>(peers, d); ballot_step<5>(peers, d); ballot_step<6>(peers, d); ballot_step<7>(peers, d);
     return peers;
 }
 
