@@ -87,7 +87,8 @@ else:
 full_table(rep, "# state after 100 steps (scripts/profile_step.py --pre 100): mean candidates 116, mean neighbours 25.")
 dev = (h2, units, d2, jx, names)
 if early is not None:
-    full_table(early, "# state after 3 steps (--pre 3, the undisturbed lattice: the sparse regime): mean candidates 39, mean neighbours 7.")
+    full_table(early, "# state after 3 steps (--pre 3, the undisturbed lattice: the sparse regime): mean candidates 39, mean neighbours 7."
+               " (Captured before the sort's ballot step was rewritten: its k_onesweep columns are ~7 % slower than the final code.)")
 h2, units, d2, jx, names = dev   # the traffic file below describes the developed state
 (out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
 
