@@ -253,7 +253,9 @@ class SlabDriver:
         b = self.b
         if not hasattr(self, "_nb_dev"):
             self._nb_dev = torch.zeros((2, 8), dtype=torch.int32, device=b.counts.device)
-            self._nb_host = torch.zeros((2, 8), dtype=torch.int32).pin_memory()
+            self._nb_host = torch.zeros((2, 8), dtype=torch.int32)
+            if b.counts.is_cuda:
+                self._nb_host = self._nb_host.pin_memory()
         mine = b.counts[lo:hi]
         sends, recvs = [], []
         if self.down is not None:
@@ -274,13 +276,15 @@ class SlabDriver:
             b.build_async()
             self._mark("build issue")
             self._neighbour_counts(0, 4)
-            counts_ready = torch.cuda.Event()
-            counts_ready.record()
+            counts_ready = torch.cuda.Event() if b.counts.is_cuda else None   # (CPU stand-in: synchronous)
+            if counts_ready is not None:
+                counts_ready.record()
             if split and self._guess is not None and self._guess[1] > self._guess[0]:
                 spec = self._guess
                 b.density_part(0, spec)   # keeps the GPU busy across the host round trip below
             self._mark("count exchange 1 issue")
-            counts_ready.synchronize()
+            if counts_ready is not None:
+                counts_ready.synchronize()
             info = b.build_finish()
             self._mark("sync 1 (build + counts)")
             nb = self._nb_host

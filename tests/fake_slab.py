@@ -102,3 +102,117 @@ class FakeSlab:
         live = np.nonzero(~self.dead[:self.n_total])[0]
         p = self.cur_pos[live].numpy()
         return p[:, 3].copy().view(np.uint32), p[:, :3].copy(), self.cur_vel[live, :3].numpy().copy()
+
+
+class FastFakeSlab(FakeSlab):
+    """The split protocol of the library on the CPU: device-side counts (`counts`), build / force
+    in _async + _finish halves, and density / force in interior + boundary parts over particle
+    CTAs of 128 (sph_slab_interior_ctas, sph_slab_density_part, sph_slab_force_part).  A part only
+    commits the particles of its own CTAs and works with the ghost data present at that moment,
+    so a driver that runs a part too early, or with a wrong interior range, gets wrong physics."""
+    CTA = 128
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.counts = torch.zeros(8, dtype=torch.int32)
+        self.emig_capacity = len(self.emig_pos[0])
+
+    # -- build -------------------------------------------------------------------------
+    def build_async(self):
+        self._info = self.build()
+        i = self._info
+        self.counts[:4] = torch.tensor([i.lo_first, i.lo_first + i.lo_count, i.hi_first, i.hi_first + i.hi_count],
+                                       dtype=torch.int32)
+        # nothing of this step has arrived yet: stale ghost slots must not be trusted
+        self.srt_pos[:self.slot0] = float("nan")
+        self.srt_pos[self.slot0 + self.n_owned:] = float("nan")
+        self.pa[:self.slot0] = float("nan")
+        self.pa[self.slot0 + self.n_owned:] = float("nan")
+        self._rho = np.full(self.n_owned, np.nan, np.float32)
+        self._f = np.full((self.n_owned, 3), np.nan, np.float32)
+
+    def build_finish(self):
+        return self._info
+
+    def interior_ctas(self):
+        i, n, C = self._info, self.n_owned, self.CTA
+        lo_end = i.lo_first + i.lo_count - self.slot0 if i.lo_count else 0
+        hi_first = i.hi_first - self.slot0 if i.hi_count else n     # (an empty layer starts at the end)
+        total = (n + C - 1) // C
+        a = min((max(lo_end, 0) + C - 1) // C, total)
+        b = max(min(hi_first, n), 0) // C
+        return a, max(a, b)
+
+    def _members(self, part, ctas):
+        n, C = self.n_owned, self.CTA
+        total = (n + C - 1) // C
+        a, b = min(ctas[0], total), min(max(ctas[1], ctas[0]), total)
+        inside = np.zeros(n, bool)
+        inside[a * C:min(b * C, n)] = True
+        return inside if part == 0 else ~inside
+
+    # -- density -----------------------------------------------------------------------
+    def density_part(self, part, ctas, g_lo=0, g_hi=0):
+        if part == 1:
+            self.g = (g_lo, g_hi)
+        g = (0, 0) if part == 0 else (g_lo, g_hi)          # the interior part may not look at ghosts
+        sl, off = self._combined(*g)
+        pos = self.srt_pos[sl, :3].numpy().copy()
+        rho, prs, _, _ = self.o.density(pos, counts=False)
+        own = slice(off, off + self.n_owned)
+        m = self._members(part, ctas)
+        pa = np.stack([prs[own], np.float32(-0.01) / rho[own]], 1).astype(np.float32)
+        idx = torch.from_numpy(np.nonzero(m)[0] + self.slot0)
+        self.pa[idx] = torch.from_numpy(pa[m])
+        self._rho[m] = rho[own][m]
+
+    # -- force -------------------------------------------------------------------------
+    def force_part(self, part, ctas):
+        g = (0, 0) if part == 0 else self.g
+        sl, off = self._combined(*g)
+        n = self.n_owned
+        pos = self.srt_pos[sl, :3].numpy().copy()
+        vel = self.srt_vel[sl, :3].numpy().copy()
+        pa = self.pa[sl].numpy()
+        prs, rho = pa[:, 0].copy(), (np.float32(-0.01) / pa[:, 1]).astype(np.float32)
+        rho[off:off + n] = self._rho
+        m = self._members(part, ctas)
+        self._f[m] = self.o.forces(pos, vel, rho, prs)[off:off + n][m]
+        if part == 1:
+            self._pending = self._integrate()
+
+    def _integrate(self):
+        import ctypes as C
+        n, s0 = self.n_owned, self.slot0
+        assert not np.isnan(self._f).any() and not np.isnan(self._rho).any(), "a part was skipped or ran too early"
+        p1 = self.srt_pos[s0:s0 + n, :3].numpy().copy()
+        v1 = self.srt_vel[s0:s0 + n, :3].numpy().copy()
+        P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(C.c_float))
+        f, rho = np.ascontiguousarray(self._f), np.ascontiguousarray(self._rho)
+        CpuOracle(n).L.oracle_integrate(P(p1), P(v1), P(f), P(rho), n, C.byref(self.o.s))
+        self.cur_pos[:n, :3] = torch.from_numpy(p1)
+        self.cur_pos[:n, 3] = self.srt_pos[s0:s0 + n, 3]
+        self.cur_vel[:n, :3] = torch.from_numpy(v1)
+        cz = self._cz(p1)
+        down, up = np.nonzero(cz < self.zlo)[0], np.nonzero(cz >= self.zhi)[0]
+        for side, idx in ((0, down), (1, up)):
+            self.emig_pos[side][:len(idx)] = self.cur_pos[idx]
+            self.emig_vel[side][:len(idx)] = self.cur_vel[idx]
+        self.dead[:] = False
+        self.dead[down] = True
+        self.dead[up] = True
+        self.counts[4:6] = torch.tensor([len(down), len(up)], dtype=torch.int32)
+        return SlabInfo(n - len(down) - len(up), n, s0, emig_down=len(down), emig_up=len(up))
+
+    def force_async(self):   # whole-slab form (driver without overlap)
+        self.density_rho_from_whole()
+        self._pending = None
+        info = self.force()
+        self.counts[4:6] = torch.tensor([info.emig_down, info.emig_up], dtype=torch.int32)
+        self._pending = info
+
+    def density_rho_from_whole(self):
+        pass   # FakeSlab.density() already left self.rho for FakeSlab.force()
+
+    def force_finish(self):
+        return self._pending

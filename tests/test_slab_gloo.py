@@ -36,18 +36,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, pos, vel, steps, out):
+def _worker(rank, world, port, pos, vel, steps, out, mode="gather"):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
-    from fake_slab import FakeSlab
+    from fake_slab import FakeSlab, FastFakeSlab
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ranges = slab_ranges(100, world)
     mine = partition(pos, 0.1, ranges)[rank]
-    b = FakeSlab(*ranges[rank], 100, capacity=len(pos), ghost_capacity=len(pos), emig_capacity=len(pos))
+    cls = FakeSlab if mode == "gather" else FastFakeSlab
+    b = cls(*ranges[rank], 100, capacity=len(pos), ghost_capacity=len(pos), emig_capacity=len(pos))
     b.load(pos[mine], vel[mine], mine.astype(np.uint32))
-    drv = SlabDriver(b, rank, world)
-    for _ in range(steps):
+    drv = SlabDriver(b, rank, world, overlap=(mode == "overlap"))
+    drv.guess_margin = 1                       # the test slabs have only a few particle CTAs
+    for k in range(steps):
+        if mode == "overlap" and k == 3:
+            drv._guess = (0, 10 ** 6)          # a wrong guess: must be detected and redone
         drv.step()
     ids, p, v = b.download()
     out[rank] = (ids, p, v, drv.stats)
@@ -55,8 +59,12 @@ def _worker(rank, world, port, pos, vel, steps, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_two_slabs_match_undecomposed_oracle(world):
+@pytest.mark.parametrize("world,mode", [(2, "gather"), (3, "gather"), (2, "neighbour"), (2, "overlap"), (3, "overlap")])
+def test_two_slabs_match_undecomposed_oracle(world, mode):
+    """mode: gather = counts through all_gather (any backend); neighbour = the library's protocol
+    (device-side counts sent to the two neighbours only, _async / _finish halves); overlap = that
+    plus interior / boundary parts with the speculative interior density and one injected wrong
+    guess."""
     from oracle.oracle import CpuOracle
     # a blob straddling the slab boundary at z = 5.0 (and 3.4 / 6.7 for three slabs), moving in z
     rng = np.random.default_rng(5)
@@ -70,7 +78,7 @@ def test_two_slabs_match_undecomposed_oracle(world):
         o.step()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), pos, vel, steps, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), pos, vel, steps, out, mode), nprocs=world, join=True)
     ids = np.concatenate([out[r][0] for r in range(world)])
     p = np.concatenate([out[r][1] for r in range(world)])
     v = np.concatenate([out[r][2] for r in range(world)])
@@ -80,3 +88,7 @@ def test_two_slabs_match_undecomposed_oracle(world):
     np.testing.assert_allclose(v[order], o.vel, rtol=1e-3, atol=1e-3)
     assert sum(out[r][3]["migrated_particles"] for r in range(world)) > 0   # migration exercised
     assert sum(out[r][3]["ghost_particles"] for r in range(world)) > 0     # halos exercised
+    if mode == "overlap":
+        hits = [out[r][3].get("speculative_hits", 0) for r in range(world)]
+        # guesses were used (slabs with enough particle CTAs), and the injected wrong one was rejected
+        assert max(hits) > 0 and all(h <= steps - 2 for h in hits), hits
