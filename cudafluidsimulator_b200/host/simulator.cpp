@@ -25,6 +25,9 @@ SphOptions options_from_env() {
     if (const char *k = std::getenv("SPH_KEY_MODE"))
         o.key_mode = (std::strcmp(k, "morton") == 0) ? SPH_KEY_MORTON : SPH_KEY_FLAT;
     if (const char *d = std::getenv("SPH_DEVICE")) o.device = std::atoi(d);
+    // opt-in: simulate() overlaps the host copy of step k with the computation of step k+1
+    // (same positions; mouse pushes then land one step later, see SphOptions.pipeline_readback)
+    if (const char *r = std::getenv("SPH_PIPELINE_READBACK")) o.pipeline_readback = std::atoi(r) != 0;
     return o;
 }
 
