@@ -47,7 +47,7 @@ class SphOptions(C.Structure):
         ("no_mask_handoff", C.c_int32),
         ("nz_cells", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32),
         ("pipeline_readback", C.c_int32), ("stage_tiles", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("density_sum", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

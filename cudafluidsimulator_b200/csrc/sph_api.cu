@@ -41,6 +41,8 @@ int fail(int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                              \
     } while (0)
 
+constexpr int kDefaultDensityExact = 0;   // SphOptions.density_sum == 0: the factored sum
+
 enum Stage { kStHash = 0, kStHist, kStSort, kStReorder, kStDensity, kStForce, kStPush, kStOther };
 const char *kStageNames[SPH_STAGE_COUNT] = {"hash",    "histogram",       "sort_passes", "reorder_cellstart",
                                             "density", "force_integrate", "push",        "other"};
@@ -79,6 +81,8 @@ struct sph_sim {
     bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
     cudaGraphExec_t graph = nullptr;       // step graph writing out_buf[0]
     cudaGraphExec_t graph_alt = nullptr;   // same step writing out_buf[1] (pipelined readback)
+    cudaGraphExec_t graph_noout = nullptr; // same step without the id-ordered position copy (sph_advance)
+    bool out_stale = false;                // out_buf[0] is older than the state (see k_unpermute)
     cudaGraphExec_t graph_build = nullptr, graph_update = nullptr;   // the two halves, for the timed step
     float *out_buf[2] = {nullptr, nullptr};
     int out_parity = 0;
@@ -162,7 +166,7 @@ int graph_launches_per_step(const sph_sim *s) { return 1 /*hist*/ + s->passes + 
 int enqueue_step(sph_sim *s) {
     const bool want_graph = s->opt.use_graph != 2 && !s->profiling;
     if (want_graph && s->keys_valid) {
-        cudaGraphExec_t &graph_slot = s->out_parity ? s->graph_alt : s->graph;
+        cudaGraphExec_t &graph_slot = !s->d.out_pos ? s->graph_noout : (s->out_parity ? s->graph_alt : s->graph);
         if (!graph_slot) {
             cudaGraph_t g = nullptr;
             const int64_t l0 = s->launches;
@@ -189,6 +193,7 @@ int enqueue_step(sph_sim *s) {
         enqueue_update(s);
     }
     s->step_valid = true;
+    s->out_stale = s->d.out_pos == nullptr;
     return 0;
 }
 
@@ -237,7 +242,8 @@ void drop_graph(sph_sim *s) {
     if (s->graph_alt) cudaGraphExecDestroy(s->graph_alt);
     if (s->graph_build) cudaGraphExecDestroy(s->graph_build);
     if (s->graph_update) cudaGraphExecDestroy(s->graph_update);
-    s->graph = s->graph_alt = s->graph_build = s->graph_update = nullptr;
+    if (s->graph_noout) cudaGraphExecDestroy(s->graph_noout);
+    s->graph = s->graph_alt = s->graph_build = s->graph_update = s->graph_noout = nullptr;
 }
 
 float bisect_sqrt_threshold(float target, bool smallest_ge) {
@@ -268,11 +274,20 @@ int free_device(sph_sim *s) {
     cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
     cudaFree(d.key); cudaFree(d.pairs[0]); cudaFree(d.pairs[1]); cudaFree(d.cell_start);
     cudaFree(d.pa); cudaFree(d.rho); cudaFree(d.force); cudaFree(s->out_buf[0]); cudaFree(s->out_buf[1]);
+    s->out_buf[0] = s->out_buf[1] = nullptr;
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_step) cudaEventDestroy(s->ev_step);
     if (s->ev_build) cudaEventDestroy(s->ev_build);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    s->copy_stream = nullptr;
+    s->ev_step = s->ev_build = s->ev_copy = nullptr;
     cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits); cudaFree(d.pair_xy); cudaFree(d.pair_z);
+    for (int sd = 0; sd < 2; ++sd) { cudaFree(d.emig_pos[sd]); cudaFree(d.emig_vel[sd]); }
+    cudaFree(s->slab_counts);   // d.emig_count points into it
+    if (s->slab_counts_host) cudaFreeHost(s->slab_counts_host);
+    s->slab_counts = s->slab_counts_host = nullptr;
+    cudaFree(s->p.dbg);
+    s->p.dbg = nullptr;
     memset(&d, 0, sizeof(d));
     if (s->host_pos) cudaFreeHost(s->host_pos);
     s->host_pos = nullptr;
@@ -302,6 +317,7 @@ int upload_state(sph_sim *s, const float *pos, const float *vel) {
     s->keys_valid = false;
     s->step_valid = false;
     s->spec_inflight = false;
+    s->out_stale = true;
     return 0;
 }
 
@@ -359,6 +375,11 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
         const int bad = s->opt.key_mode;
         delete s;
         return fail(SPH_E_INVALID, "unknown key_mode %d", bad);
+    }
+    if (s->opt.density_sum < 0 || s->opt.density_sum > 2) {
+        const int bad = s->opt.density_sum;
+        delete s;
+        return fail(SPH_E_INVALID, "unknown density_sum %d", bad);
     }
     memset(&s->d, 0, sizeof(s->d));
     Params &p = s->p;
@@ -423,6 +444,95 @@ void sph_destroy(sph_sim *s) {
     delete s;
 }
 
+// Device half of sph_setup(); on failure the caller releases whatever was allocated.
+static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
+    const SphSettings &st = s->settings;
+    (void)st;
+    // -- device ---------------------------------------------------------------
+    CU(cudaSetDevice(s->opt.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, s->opt.device));
+    if (prop.major < 10)
+        return fail(SPH_E_INVALID, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    s->opt.device, prop.major, prop.minor);
+    s->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)(s->capacity > 0 ? s->capacity : 1);
+    DeviceState &d = s->d;
+    size_t scap = cap;   // sorted-slot capacity: owned + ghost room on both sides in slab mode
+    if (s->p.slab) {
+        int g = s->opt.ghost_capacity > 0 ? s->opt.ghost_capacity : (int)(cap / 4) + 1024;
+        g = (g + 1) & ~1;   // slot0 must be even (pair-interleaved copy)
+        s->ghost_cap = g;
+        s->p.slot0 = g;
+        scap = cap + 2 * (size_t)g;
+        d.emig_capacity = s->opt.emig_capacity > 0 ? s->opt.emig_capacity : (int)(cap / 16) + 1024;
+        for (int sd = 0; sd < 2; ++sd) {
+            CU(cudaMalloc(&d.emig_pos[sd], (size_t)d.emig_capacity * sizeof(float4)));
+            CU(cudaMalloc(&d.emig_vel[sd], (size_t)d.emig_capacity * sizeof(float4)));
+        }
+        CU(cudaMalloc(&s->slab_counts, 8 * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(s->slab_counts, 0, 8 * sizeof(uint32_t), s->stream));
+        CU(cudaMallocHost(&s->slab_counts_host, 8 * sizeof(uint32_t)));
+        d.emig_count = s->slab_counts + 4;
+    }
+    CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_pos, scap * sizeof(float4)));
+    CU(cudaMalloc(&d.srt_vel, scap * sizeof(float4)));
+    CU(cudaMalloc(&d.key, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.pairs[0], cap * sizeof(uint64_t)));
+    CU(cudaMalloc(&d.pairs[1], cap * sizeof(uint64_t)));
+    CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.pa, scap * sizeof(float2)));
+    CU(cudaMalloc(&d.rho, scap * sizeof(float)));
+    if (!s->p.slab) {
+        CU(cudaMalloc(&s->out_buf[0], cap * 3 * sizeof(float)));
+        d.out_pos = s->out_buf[0];
+        if (s->opt.pipeline_readback) {
+            CU(cudaMalloc(&s->out_buf[1], cap * 3 * sizeof(float)));
+            CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
+        }
+    }
+    CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
+    CU(cudaMalloc(&s->p.dbg, sizeof(uint32_t)));
+    CU(cudaMemsetAsync(s->p.dbg, 0, sizeof(uint32_t), s->stream));
+    if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
+    if (s->p.key_mode == SPH_KEY_FLAT) {
+        // + 2 records: the staged tiles copy even-aligned pair ranges
+        CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2 + 2) * sizeof(float4)));
+        CU(cudaMalloc(&d.pair_z, ((scap + 1) / 2 + 2) * sizeof(float2)));
+        CU(cudaMemsetAsync(d.pair_xy, 0, ((scap + 1) / 2 + 2) * sizeof(float4), s->stream));
+        CU(cudaMemsetAsync(d.pair_z, 0, ((scap + 1) / 2 + 2) * sizeof(float2), s->stream));
+        d.stage_tiles = s->opt.stage_tiles ? 1 : 0;
+        d.density_exact = s->opt.density_sum == 2 ? 0 : (s->opt.density_sum == 1 ? 1 : kDefaultDensityExact);
+    }
+    if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
+        const size_t ctas = (cap + kBlock - 1) / kBlock;
+        CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));
+    }
+    CU(cudaMemsetAsync(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t), s->stream));
+    CU(cudaMemsetAsync(d.rho, 0, scap * sizeof(float), s->stream));
+    if (!s->p.slab) {
+        CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
+        memset(s->host_pos, 0, cap * 3 * sizeof(float));
+    } else {
+        s->p.n = 0;
+    }
+    // every clear above ran on the simulator's own stream (it is non-blocking: the legacy default
+    // stream would not be ordered against it)
+    CU(cudaStreamSynchronize(s->stream));
+    if (n > 0) {
+        int rc = upload_state(s, pos.data(), nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+
 // ref: simulator.cu:411-460
 int sph_setup(sph_sim *s) {
     if (!s) return fail(SPH_E_INVALID, "null simulator handle");
@@ -465,84 +575,14 @@ int sph_setup(sph_sim *s) {
                 }
     }
 
-    // -- device ---------------------------------------------------------------
-    CU(cudaSetDevice(s->opt.device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, s->opt.device));
-    if (prop.major < 10)
-        return fail(SPH_E_INVALID, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
-                    s->opt.device, prop.major, prop.minor);
-    s->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    const size_t cap = (size_t)(s->capacity > 0 ? s->capacity : 1);
-    DeviceState &d = s->d;
-    size_t scap = cap;   // sorted-slot capacity: owned + ghost room on both sides in slab mode
-    if (s->p.slab) {
-        int g = s->opt.ghost_capacity > 0 ? s->opt.ghost_capacity : (int)(cap / 4) + 1024;
-        g = (g + 1) & ~1;   // slot0 must be even (pair-interleaved copy)
-        s->ghost_cap = g;
-        s->p.slot0 = g;
-        scap = cap + 2 * (size_t)g;
-        d.emig_capacity = s->opt.emig_capacity > 0 ? s->opt.emig_capacity : (int)(cap / 16) + 1024;
-        for (int sd = 0; sd < 2; ++sd) {
-            CU(cudaMalloc(&d.emig_pos[sd], (size_t)d.emig_capacity * sizeof(float4)));
-            CU(cudaMalloc(&d.emig_vel[sd], (size_t)d.emig_capacity * sizeof(float4)));
-        }
-        CU(cudaMalloc(&s->slab_counts, 8 * sizeof(uint32_t)));
-        CU(cudaMemset(s->slab_counts, 0, 8 * sizeof(uint32_t)));
-        CU(cudaMallocHost(&s->slab_counts_host, 8 * sizeof(uint32_t)));
-        d.emig_count = s->slab_counts + 4;
-    }
-    CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
-    CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
-    CU(cudaMalloc(&d.srt_pos, scap * sizeof(float4)));
-    CU(cudaMalloc(&d.srt_vel, scap * sizeof(float4)));
-    CU(cudaMalloc(&d.key, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&d.pairs[0], cap * sizeof(uint64_t)));
-    CU(cudaMalloc(&d.pairs[1], cap * sizeof(uint64_t)));
-    CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&d.pa, scap * sizeof(float2)));
-    CU(cudaMalloc(&d.rho, scap * sizeof(float)));
-    if (!s->p.slab) {
-        CU(cudaMalloc(&s->out_buf[0], cap * 3 * sizeof(float)));
-        d.out_pos = s->out_buf[0];
-        if (s->opt.pipeline_readback) {
-            CU(cudaMalloc(&s->out_buf[1], cap * 3 * sizeof(float)));
-            CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
-        }
-    }
-    CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
-    CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
-    CU(cudaMalloc(&s->p.dbg, sizeof(uint32_t)));
-    CU(cudaMemset(s->p.dbg, 0, sizeof(uint32_t)));
-    if (s->opt.record_force) CU(cudaMalloc(&d.force, scap * sizeof(float4)));
-    if (s->p.key_mode == SPH_KEY_FLAT) {
-        // + 2 records: the staged tiles copy even-aligned pair ranges
-        CU(cudaMalloc(&d.pair_xy, ((scap + 1) / 2 + 2) * sizeof(float4)));
-        CU(cudaMalloc(&d.pair_z, ((scap + 1) / 2 + 2) * sizeof(float2)));
-        CU(cudaMemset(d.pair_xy, 0, ((scap + 1) / 2 + 2) * sizeof(float4)));
-        CU(cudaMemset(d.pair_z, 0, ((scap + 1) / 2 + 2) * sizeof(float2)));
-        d.stage_tiles = s->opt.stage_tiles ? 1 : 0;
-    }
-    if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
-        const size_t ctas = (cap + kBlock - 1) / kBlock;
-        CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));
-    }
-    CU(cudaMemset(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
-    CU(cudaMemset(d.rho, 0, scap * sizeof(float)));
-    if (!s->p.slab) {
-        CU(cudaMallocHost(&s->host_pos, cap * 3 * sizeof(float)));
-        memset(s->host_pos, 0, cap * 3 * sizeof(float));
-    } else {
-        s->p.n = 0;
+    int rc = setup_device(s, n, pos);
+    if (rc) {   // leave nothing behind: a retried sph_setup() starts from scratch
+        free_device(s);
+        if (s->stream && s->own_stream) cudaStreamDestroy(s->stream);
+        s->stream = nullptr;
+        return rc;
     }
     s->is_setup = true;
-    if (n > 0) {
-        int rc = upload_state(s, pos.data(), nullptr);
-        if (rc) return rc;
-    }
     return 0;
 }
 
@@ -574,11 +614,23 @@ static int step_pipelined(sph_sim *s) {
     return 0;
 }
 
+// A pipelined sph_step() left one more step enqueued than it handed out (its positions are in
+// out_buf[out_parity]).  The other stepping calls count that step as their first one, so that
+// mixing them with pipelined sph_step() advances the state by exactly the steps asked for.
+// Returns 1 if such a step was consumed.
+static int take_speculative_step(sph_sim *s) {
+    if (!s->spec_inflight) return 0;
+    s->spec_inflight = false;
+    return 1;
+}
+
 int sph_step(sph_sim *s) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
     if (s->opt.pipeline_readback) return step_pipelined(s);
+    s->d.out_pos = s->out_buf[0];
+    s->out_parity = 0;
     int rc = enqueue_step(s);
     if (rc) return rc;
     // ref: simulator.cu:478-480 -- blocking copy of every position to the host
@@ -591,30 +643,40 @@ int sph_step(sph_sim *s) {
 int sph_step_timed(sph_sim *s, SphTimes *times) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
-    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (!times) return fail(SPH_E_INVALID, "null times");
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a) {
         return std::chrono::duration_cast<std::chrono::duration<double>>(clk::now() - a).count();
     };
     if (s->p.n > 0) {
-        s->d.out_pos = s->out_buf[0];
-        s->out_parity = 0;
-        auto t0 = clk::now();
-        int rc = enqueue_half(s, true);
-        if (rc == 0) rc = sync_stream(s);
-        if (rc) return rc;
-        times->buildGrid += secs(t0);
+        int rc = 0;
+        if (take_speculative_step(s)) {
+            // the step is already on the stream (enqueued by a pipelined sph_step): its device time
+            // cannot be split into the two buckets any more, it is charged to "SPH update"
+            auto t1 = clk::now();
+            rc = sync_stream(s);
+            if (rc) return rc;
+            times->sphUpdate += secs(t1);
+        } else {
+            s->d.out_pos = s->out_buf[0];
+            s->out_parity = 0;
+            auto t0 = clk::now();
+            rc = enqueue_half(s, true);
+            if (rc == 0) rc = sync_stream(s);
+            if (rc) return rc;
+            times->buildGrid += secs(t0);
 
-        auto t1 = clk::now();
-        rc = enqueue_half(s, false);
-        if (rc == 0) rc = sync_stream(s);
-        if (rc) return rc;
-        times->sphUpdate += secs(t1);
-        s->step_valid = true;
+            auto t1 = clk::now();
+            rc = enqueue_half(s, false);
+            if (rc == 0) rc = sync_stream(s);
+            if (rc) return rc;
+            times->sphUpdate += secs(t1);
+            s->step_valid = true;
+            s->out_stale = false;
+        }
 
         auto t2 = clk::now();
-        CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
+        CU(cudaMemcpyAsync(s->host_pos, s->out_buf[s->out_parity], sizeof(float) * 3 * (size_t)s->p.n,
                            cudaMemcpyDeviceToHost, s->stream));
         rc = sync_stream(s);
         if (rc) return rc;
@@ -627,9 +689,10 @@ int sph_step_timed(sph_sim *s, SphTimes *times) {
 int sph_advance(sph_sim *s, int steps) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
-    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (steps < 0) return fail(SPH_E_INVALID, "steps < 0");
     if (s->p.n == 0) return 0;
+    if (steps > 0) steps -= take_speculative_step(s);
+    s->d.out_pos = nullptr;   // positions in id order are produced on demand (sph_readback)
     for (int k = 0; k < steps; ++k) {
         int rc = enqueue_step(s);
         if (rc) return rc;
@@ -640,13 +703,18 @@ int sph_advance(sph_sim *s, int steps) {
 int sph_advance_timed(sph_sim *s, int steps, float *ms) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
-    s->spec_inflight = false;   // positions of a speculative step are not handed out
     if (steps < 0 || !ms) return fail(SPH_E_INVALID, "bad argument");
+    if (take_speculative_step(s)) {   // timing starts from a quiet stream, with the pending step counted
+        int rc = sync_stream(s);
+        if (rc) return rc;
+        if (steps > 0) --steps;
+    }
     cudaEvent_t a, b;
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, s->stream));
     int rc = 0;
+    s->d.out_pos = nullptr;
     for (int k = 0; k < steps && rc == 0 && s->p.n > 0; ++k) rc = enqueue_step(s);
     cudaEventRecord(b, s->stream);
     if (rc == 0) rc = sync_stream(s);
@@ -674,9 +742,18 @@ int sph_readback(sph_sim *s) {
     REQUIRE_SETUP(s);
     NOT_IN_SLAB_MODE(s);
     if (s->p.n == 0) return 0;
-    s->spec_inflight = false;   // the host buffer now shows the internal (latest) step
-    CU(cudaMemcpyAsync(s->host_pos, s->d.out_pos, sizeof(float) * 3 * (size_t)s->p.n,
-                       cudaMemcpyDeviceToHost, s->stream));
+    take_speculative_step(s);   // the host buffer now shows the internal (latest) step
+    float *src = s->out_buf[s->out_parity];
+    if (s->out_stale) {         // the last steps ran without the id-ordered copy: make it now
+        src = s->out_buf[0];
+        s->out_parity = 0;
+        stage_begin(s, kStOther);
+        launch_unpermute(s->p, s->d, src, s->stream);
+        stage_end(s);
+        s->out_stale = false;
+    }
+    CU(cudaMemcpyAsync(s->host_pos, src, sizeof(float) * 3 * (size_t)s->p.n, cudaMemcpyDeviceToHost,
+                       s->stream));
     return sync_stream(s);
 }
 

@@ -25,6 +25,8 @@ struct DeviceState {
     int32_t *counts;             // optional 2*n scratch for K and C
     const uint64_t *sorted_pairs;  // pairs[sorted buffer] of this step: key of sorted slot i in the high word
     int stage_tiles;             // 1: dense CTAs run k_density_tile (TMA-staged neighbour tiles)
+    int density_exact;           // 1: density summed term by term in the reference's order (bit-identical
+                                 // to the CPU restatement); 0: factored sum (DensityAcc in sph_kernels.cu)
     uint32_t *nbits;             // in-range bit masks density hands to force; kMaskWords words
                                  // per particle, [CTA][word][lane] interleaved
     // slab mode: particles that left the owned z-layers during integration, per side
@@ -50,6 +52,8 @@ void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int n
 void launch_density(const Params &p, const Thresholds &t, const DeviceState &d, bool counts,
                     cudaStream_t s);
 void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);
+// positions of the state (cur_pos, id in .w) -> xyz packed in ORIGINAL particle order
+void launch_unpermute(const Params &p, const DeviceState &d, float *out_pos, cudaStream_t s);
 void launch_push(const Params &p, const DeviceState &d, int click_x, int click_y, cudaStream_t s);
 void launch_stats(const Params &p, const DeviceState &d, cudaStream_t s);
 // slab mode: hash of freshly appended particles [first, first+count) of the cur arrays

@@ -73,7 +73,7 @@ class SlabBackend:
     """The B200 library in slab mode (libsph_b200.so, sph_slab_* entry points)."""
 
     def __init__(self, settings, zlo, zhi, nz, capacity, device=0, ghost_capacity=0,
-                 emig_capacity=0):
+                 emig_capacity=0, density_sum=0):
         from . import _native as N
         self.N = N
         self.lib = N.load()
@@ -84,6 +84,7 @@ class SlabBackend:
         opt.capacity = int(capacity)
         opt.z_cell_lo, opt.z_cell_hi, opt.nz_cells = int(zlo), int(zhi), int(nz)
         opt.ghost_capacity, opt.emig_capacity = int(ghost_capacity), int(emig_capacity)
+        opt.density_sum = int(density_sum)
         cs = settings.to_c()
         cs.numParticles = 0
         h = C.c_void_p()

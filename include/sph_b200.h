@@ -98,7 +98,12 @@ typedef struct SphOptions {
     int32_t stage_tiles;  /* 1: dense CTAs (128 consecutive particles within a few cells of one
                              row) compute density out of neighbour tiles staged in shared memory
                              by bulk TMA (A/B switch; see DESIGN.md 3.4 for the measurement)    */
-    int32_t reserved[3];
+    int32_t density_sum;  /* how a particle's density terms are added up: 0 = library default,
+                             1 = term by term in the reference's loop order (bit-identical to the
+                             serial restatement of simulator.cu:163-185), 2 = factored,
+                             rho = (m dk) * sum (h^2 - r^2)^3 with two interleaved partial sums (a few
+                             ulp away; the reference's own order is its CAS race order)           */
+    int32_t reserved[2];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */

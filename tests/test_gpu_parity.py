@@ -6,8 +6,10 @@ density, force and position within a stated FP32 relative tolerance; multi-step
 aggregates within a stated bound.
 
   integers (keys, order, cell table, K, C)            bit-exact
-  density, pressure                                   bit-exact vs the oracle (same
-                                                      arithmetic, same visiting order)
+  density, pressure                                   density_sum=1 (the reference's term-by-term
+                                                      sum): bit-exact vs the oracle (same
+                                                      arithmetic, same visiting order);
+                                                      default (factored sum): rtol 2e-6
   force            |dF| <= 1e-5 * max(|F|, sum|terms|) per component
   position         rtol 1e-5 / atol 1e-6 after one step
 """
@@ -25,9 +27,12 @@ RTOL_POS = 1e-5
 RTOL_F = 1e-5
 
 
-def make(n, key_mode=sph.SPH_KEY_FLAT, **kw):
+RTOL_RHO = 2e-6   # density / pressure when the sum is not formed in the oracle's order
+
+
+def make(n, key_mode=sph.SPH_KEY_FLAT, density_sum=0, **kw):
     s = sph.Settings(numParticles=n, **kw)
-    sim = sph.Simulator(s, key_mode=key_mode, record_force=True)
+    sim = sph.Simulator(s, key_mode=key_mode, record_force=True, density_sum=density_sum)
     sim.setup()
     return sim
 
@@ -78,24 +83,25 @@ def test_keys_order_counts_bit_exact(name, mode):
 
 
 @pytest.mark.parametrize("name", list(STATES))
-@pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
-def test_single_step_density_force_position(name, mode):
+@pytest.mark.parametrize("mode,density_sum", [(sph.SPH_KEY_FLAT, 0), (sph.SPH_KEY_FLAT, 1), (sph.SPH_KEY_MORTON, 0)],
+                         ids=["flat", "flat-refsum", "morton"])
+def test_single_step_density_force_position(name, mode, density_sum):
     pos, vel = STATES[name]()
     n = len(pos)
     o = CpuOracle(n)
     o.set_state(pos, vel)
     o.step()
-    sim = make(n, key_mode=mode)
+    sim = make(n, key_mode=mode, density_sum=density_sum)
     sim.set_state(pos, vel)
     sim.simulate()
     rho, prs, f = sim.get_density_pressure_force()
-    if mode == sph.SPH_KEY_FLAT:
+    if mode == sph.SPH_KEY_FLAT and density_sum == 1:
         # same arithmetic and same visiting order as the oracle: bit-exact
         np.testing.assert_array_equal(rho, o.rho)
         np.testing.assert_array_equal(prs, o.prs)
     else:
-        np.testing.assert_allclose(rho, o.rho, rtol=2e-6, atol=0)
-        np.testing.assert_allclose(prs, o.prs, rtol=0, atol=2e-6 * float(o.rho.max()))
+        np.testing.assert_allclose(rho, o.rho, rtol=RTOL_RHO, atol=0)
+        np.testing.assert_allclose(prs, o.prs, rtol=0, atol=RTOL_RHO * float(o.rho.max()))
     tol = force_tolerance(o, pos, vel, o.rho, o.prs, rel=RTOL_F)
     err = np.abs(f - o.force)
     assert np.all(err <= tol), f"force: worst excess {np.max(err / tol):.3g}x tolerance"
