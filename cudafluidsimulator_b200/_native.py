@@ -65,6 +65,25 @@ class SphSlabBuffers(C.Structure):
                 ("capacity", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32)]
 
 
+SPH_NCCL_ID_BYTES = 128
+SPH_MAX_LOCAL_SLABS = 16
+
+
+class SphClusterOptions(C.Structure):
+    _fields_ = [("world", C.c_int32), ("first_rank", C.c_int32), ("local_count", C.c_int32),
+                ("devices", C.c_int32 * SPH_MAX_LOCAL_SLABS), ("nz_cells", C.c_int32),
+                ("capacity", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32),
+                ("density_sum", C.c_int32), ("rebalance_every", C.c_int32), ("reserved", C.c_int32 * 6),
+                ("nccl_id", C.c_uint8 * SPH_NCCL_ID_BYTES)]
+
+
+class SphSlabStats(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("device", C.c_int32), ("z_cell_lo", C.c_int32), ("z_cell_hi", C.c_int32),
+                ("n_owned", C.c_int32), ("ghosts_lo", C.c_int32), ("ghosts_hi", C.c_int32), ("steps", C.c_int32),
+                ("migrated_total", C.c_int64), ("ghosts_total", C.c_int64), ("overflow", C.c_uint32),
+                ("rebalances", C.c_int32), ("kinetic_energy", C.c_double), ("density_sum", C.c_double)]
+
+
 # every symbol include/sph_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _F = C.POINTER(C.c_float)
@@ -106,6 +125,21 @@ SYMBOLS = {
     "sph_slab_buffers": (C.c_int, [_P, C.POINTER(SphSlabBuffers)]),
     "sph_slab_download": (C.c_int, [_P, _U, _F, _F, _I]),
     "sph_set_stream": (C.c_int, [_P, C.c_void_p]),
+    "sph_cluster_nccl_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "sph_cluster_create": (C.c_int, [C.POINTER(SphSettings), C.POINTER(SphClusterOptions), C.POINTER(_P)]),
+    "sph_cluster_destroy": (None, [_P]),
+    "sph_cluster_setup": (C.c_int, [_P]),
+    "sph_cluster_load": (C.c_int, [_P, C.c_int, C.c_int, _F, _F, _U]),
+    "sph_cluster_advance": (C.c_int, [_P, C.c_int]),
+    "sph_cluster_advance_timed": (C.c_int, [_P, C.c_int, _F]),
+    "sph_cluster_step": (C.c_int, [_P]),
+    "sph_cluster_sync": (C.c_int, [_P]),
+    "sph_cluster_host_records": (C.c_int, [_P, C.c_int, C.POINTER(_F), _I]),
+    "sph_cluster_positions": (C.c_int, [_P, _F, C.c_int64]),
+    "sph_cluster_download": (C.c_int, [_P, C.c_int, _U, _F, _F, _I]),
+    "sph_cluster_stats": (C.c_int, [_P, C.c_int, C.POINTER(SphSlabStats)]),
+    "sph_cluster_rebalance": (C.c_int, [_P]),
+    "sph_cluster_launch_count": (C.c_int64, [_P]),
     "sph_debug_flags": (C.c_int, [_P, _U, _I]),
     "sph_profile_enable": (C.c_int, [_P, C.c_int]),
     "sph_profile_read": (C.c_int, [_P, _D, C.POINTER(C.c_int64), C.c_int]),

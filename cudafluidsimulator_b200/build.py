@@ -31,7 +31,7 @@ NVCC_FLAGS = [
     "-lineinfo", "--extended-lambda",
     "-Xcompiler", "-fPIC", "-shared",
 ]
-CU_SOURCES = ["sph_api.cu", "sph_kernels.cu", "sph_sort.cu"]
+CU_SOURCES = ["sph_api.cu", "sph_kernels.cu", "sph_sort.cu", "sph_cluster.cu"]
 
 
 def _nvcc() -> str:
@@ -65,7 +65,8 @@ def build_library(force: bool = False, verbose_ptxas: bool = False, checked: boo
         flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else [])
         if checked:
             flags.append("-DSPH_BOUNDS_CHECK")
-        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", target, *[CSRC / f for f in CU_SOURCES]])
+        # libdl: NCCL is resolved with dlopen when a multi-process cluster is created (sph_cluster.cu)
+        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", target, *[CSRC / f for f in CU_SOURCES], "-ldl"])
     return target
 
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/sph_b200.h"
+#include "sph_internal.cuh"
 #include "sph_kernels.cuh"
 #include "sph_sort.cuh"
 
@@ -70,6 +71,7 @@ struct sph_sim {
     bool own_stream = true;
     // slab mode
     int ghost_cap = 0;          // == p.slot0
+    uint32_t table_capacity = 0;   // cell_start entries allocated (slab: room for the layer range to grow)
     int n_total = 0;            // entries of the cur arrays in use
     int n_dead = 0;             // of which emigrated (dropped by the next build)
     int hashed_upto = 0;        // keys of cur[0, hashed_upto) are valid
@@ -269,6 +271,19 @@ float bisect_sqrt_threshold(float target, bool smallest_ge) {
     return r;
 }
 
+}  // namespace
+
+// Internal: error reporting for the other translation units of the library (sph_cluster.cu).
+extern "C" int sph_internal_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
 int free_device(sph_sim *s) {
     DeviceState &d = s->d;
     cudaFree(d.cur_pos); cudaFree(d.cur_vel); cudaFree(d.srt_pos); cudaFree(d.srt_vel);
@@ -407,7 +422,7 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
         p.zoff = p.zlo - 1;
         p.ncz = p.zhi - p.zlo + 2;
         p.hi_z = (float)nz * st->h - st->h;
-        if ((double)nc * nc * p.ncz >= (double)(1u << 30)) {
+        if ((double)nc * nc * (p.ncz + kSlabSpareLayers) >= (double)(1u << 30)) {
             delete s;
             return fail(SPH_E_INVALID, "slab too thick: nc^2 * (layers + 2) must stay below 2^30");
         }
@@ -474,7 +489,8 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
         CU(cudaMalloc(&s->slab_counts, 8 * sizeof(uint32_t)));
         CU(cudaMemsetAsync(s->slab_counts, 0, 8 * sizeof(uint32_t), s->stream));
         CU(cudaMallocHost(&s->slab_counts_host, 8 * sizeof(uint32_t)));
-        d.emig_count = s->slab_counts + 4;
+        d.emig_count[0] = s->slab_counts + 4;
+        d.emig_count[1] = s->slab_counts + 5;
     }
     CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
     CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
@@ -483,7 +499,9 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
     CU(cudaMalloc(&d.key, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&d.pairs[0], cap * sizeof(uint64_t)));
     CU(cudaMalloc(&d.pairs[1], cap * sizeof(uint64_t)));
-    CU(cudaMalloc(&d.cell_start, ((size_t)s->p.table_size + 1) * sizeof(uint32_t)));
+    // slab mode: the owned layer range may grow by a few layers when the cluster rebalances
+    s->table_capacity = s->p.table_size + (s->p.slab ? (uint32_t)s->p.nc * s->p.nc * (uint32_t)kSlabSpareLayers : 0u);
+    CU(cudaMalloc(&d.cell_start, ((size_t)s->table_capacity + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&d.pa, scap * sizeof(float2)));
     CU(cudaMalloc(&d.rho, scap * sizeof(float)));
     if (!s->p.slab) {
@@ -1073,13 +1091,13 @@ int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
 // the pinned mirror.
 int sph_slab_force_async(sph_sim *s) {
     REQUIRE_SLAB(s);
-    CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
+    CU(cudaMemsetAsync(s->slab_counts + 4, 0, 2 * sizeof(uint32_t), s->stream));
     if (s->p.n > 0) {
         stage_begin(s, kStForce);
         launch_force_integrate(s->p, s->th, s->d, s->stream);
         stage_end(s);
     }
-    CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->d.emig_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->slab_counts + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     return 0;
 }
 
@@ -1151,14 +1169,14 @@ int sph_slab_force_part(sph_sim *s, int part, int cta_a, int cta_b) {
     Params p;
     int rc = part_params(s, part, cta_a, cta_b, &p);
     if (rc) return rc;
-    if (part == 0) CU(cudaMemsetAsync(s->d.emig_count, 0, 2 * sizeof(uint32_t), s->stream));
+    if (part == 0) CU(cudaMemsetAsync(s->slab_counts + 4, 0, 2 * sizeof(uint32_t), s->stream));
     if (p.cta_count > 0) {
         stage_begin(s, kStForce);
         launch_force_integrate(p, s->th, s->d, s->stream);
         stage_end(s);
     }
     if (part == 1)
-        CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->d.emig_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->slab_counts + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     return 0;
 }
 
@@ -1208,6 +1226,24 @@ int sph_slab_download(sph_sim *s, uint32_t *ids, float *pos, float *vel, int *n_
         ++m;
     }
     if (n_out) *n_out = m;
+    return 0;
+}
+
+// Internal (declared in sph_internal.cuh, not part of the public header): what the slab cluster
+// driver (sph_cluster.cu) needs from a simulator created in slab mode.
+int sph_internal_core(sph_sim *s, sph::SlabCore *out) {
+    REQUIRE_SLAB(s);
+    out->p = &s->p;
+    out->d = &s->d;
+    out->th = &s->th;
+    out->stream = s->stream;
+    out->capacity = s->capacity;
+    out->ghost_cap = s->ghost_cap;
+    out->passes = &s->passes;
+    out->sm_count = s->sm_count;
+    out->sorted_buf = &s->sorted_buf;
+    out->device = s->opt.device;
+    out->table_capacity = s->table_capacity;
     return 0;
 }
 

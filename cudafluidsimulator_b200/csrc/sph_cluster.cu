@@ -1,0 +1,855 @@
+// sph_cluster.cu -- the SPH step across several GPUs: z-slab decomposition, per-step ghost halo
+// exchange and particle migration (north_star).  There is no reference counterpart
+// (the reference is single-GPU); the single-GPU step this builds on replaces
+// ref src/simulator.cu:462-497.
+//
+// One slab-mode simulator (sph_api.cu) per GPU owns the global cell layers [zlo, zhi) along z --
+// gravity is -y and the reference's grid init fills x-planes first, so z-slabs start balanced.
+// Keys are local to the slab (layer 0 and ncz-1 are the ghost layers).  Per step and slab, all on
+// the slab's own stream and WITHOUT any host round trip:
+//
+//   sort (n_total from device memory) -> reorder (n_live) -> pack the lowest / highest owned layer
+//   [halo A]   pos+vel of those layers -> the neighbours' ghost slots
+//   ghost install (cell ranges of the ghost layers) -> density of the owned particles
+//   [halo B]   {p, a} of the same layers -> the neighbours' ghost slots
+//   force + integrate; a particle whose new z cell leaves [zlo, zhi) is appended to the migration
+//   message of that side and gets the dead key (the next sort parks it behind the live ones)
+//   [migration] emigrants -> appended behind the neighbour's particles, keyed
+//
+// Every count (particles, boundary layers, ghosts, emigrants) stays in device memory (SlabDyn and
+// the message headers); kernels are launched over capacities.  A message is a fixed-capacity
+// buffer moved whole: between slabs of this process with cudaMemcpyPeerAsync (NVLink P2P, ordered
+// by events), between processes with ncclSend / ncclRecv on the slab's stream.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "sph_internal.cuh"
+#include "sph_sort.cuh"
+
+using namespace sph;
+
+extern "C" int sph_internal_fail(int code, const char *fmt, ...);
+
+namespace {
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return sph_internal_fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                     __FILE__, __LINE__);                                          \
+    } while (0)
+
+// ---- NCCL, resolved at run time: only a multi-process job needs it ------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names)
+        if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!h) return sph_internal_fail(SPH_E_STATE, "NCCL is needed for a multi-process cluster but libnccl.so.2 was not found: %s", dlerror());
+#define SYM(field, name)                                                                        \
+    do {                                                                                        \
+        *(void **)(&g_nccl.field) = dlsym(h, name);                                             \
+        if (!g_nccl.field) return sph_internal_fail(SPH_E_STATE, "libnccl lacks %s", name);     \
+    } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = h;
+    return 0;
+}
+
+#define NC(expr)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r__ = (expr);                                                                \
+        if (r__ != ncclSuccess)                                                                   \
+            return sph_internal_fail(SPH_E_STATE, "%s failed: %s (%s:%d)", #expr,                 \
+                                     g_nccl.GetErrorString(r__), __FILE__, __LINE__);             \
+    } while (0)
+
+enum MsgKind { kHaloA = 0, kHaloB = 1, kMigrate = 2, kMsgKinds = 3 };
+
+struct Slab {
+    sph_sim *sim = nullptr;
+    SlabCore core{};
+    int rank = 0, device = 0;
+    int zlo = 0, zhi = 0;
+    SlabDyn *dyn = nullptr;        // device
+    SlabDyn *dyn_host = nullptr;   // pinned mirror, refreshed asynchronously
+    // messages: [kind][side]; side 0 = towards / from the slab below, 1 = above
+    MsgHeader *send[kMsgKinds][2] = {};
+    MsgHeader *recv[kMsgKinds][2] = {};
+    cudaEvent_t ev_packed[kMsgKinds] = {};     // this slab's send buffers of that kind are complete
+    cudaEvent_t ev_copied[kMsgKinds][2] = {};  // this slab has copied the message of its neighbour on that side
+    bool copied_pending[kMsgKinds][2] = {};    // ... and that neighbour has not waited for it yet
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // per-step host records
+    float4 *out_stage = nullptr;   // device copy of the records, so the next step can overwrite cur_pos
+    float4 *host_records = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr;
+    bool out_pending = false;
+    int out_count = 0;
+    int known_total = 0;           // host-side bound on n_total
+    int rebalances = 0;
+    double *stats_dev = nullptr;   // 2 doubles
+    bool hashed = false;
+};
+
+}  // namespace
+
+struct sph_cluster {
+    SphSettings st{};
+    SphClusterOptions opt{};
+    int nz = 0, nc = 0;
+    int cap = 0, cap_g = 0, cap_m = 0;
+    size_t msg_bytes[kMsgKinds] = {};
+    std::vector<Slab> slabs;            // local slabs, ascending rank
+    std::vector<int> zlo, zhi;          // every rank's layer range
+    std::vector<int> max_layers;        // every rank's cell-table room, in owned layers
+    int64_t launches = 0;
+    int steps_since_rebalance = 0;
+    bool loaded = false;
+};
+
+namespace {
+
+bool is_local(const sph_cluster *c, int rank) {
+    return rank >= c->opt.first_rank && rank < c->opt.first_rank + c->opt.local_count;
+}
+Slab *local_slab(sph_cluster *c, int rank) { return &c->slabs[rank - c->opt.first_rank]; }
+
+void split_layers(int nz, int world, std::vector<int> &lo, std::vector<int> &hi) {
+    lo.resize(world);
+    hi.resize(world);
+    const int base = nz / world, extra = nz % world;
+    int z = 0;
+    for (int r = 0; r < world; ++r) {
+        const int n = base + (r < extra ? 1 : 0);
+        lo[r] = z;
+        hi[r] = z + n;
+        z += n;
+    }
+}
+
+// Layer range -> the slab's kernel parameters (keys are local: layer = z - zoff).
+void apply_range(Slab &s, int zlo, int zhi) {
+    Params &p = *s.core.p;
+    s.zlo = zlo;
+    s.zhi = zhi;
+    p.zlo = zlo;
+    p.zhi = zhi;
+    p.zoff = zlo - 1;
+    p.ncz = zhi - zlo + 2;
+    p.table_size = (uint32_t)p.nc * p.nc * (uint32_t)p.ncz;
+    p.dead_key = p.table_size - 1u;
+    *s.core.passes = sort_passes_for(p.table_size);
+}
+
+int alloc_msg(MsgHeader **out, size_t bytes) {
+    CU(cudaMalloc(out, bytes));
+    CU(cudaMemset(*out, 0, bytes));
+    return 0;
+}
+
+// ---- one exchange of one message kind between all neighbouring slabs ---------------------------
+// Local neighbour: the RECEIVER's stream waits for the sender's pack event and copies the whole
+// buffer peer to peer; the sender's next pack of that kind waits for the "taken" event.
+// Remote neighbour: ncclSend / ncclRecv of the whole buffer on the slab's own stream.
+int exchange(sph_cluster *c, int kind) {
+    const size_t bytes = c->msg_bytes[kind];
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        CU(cudaEventRecord(s.ev_packed[kind], s.core.stream));
+    }
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        bool grouped = false;
+        for (int side = 0; side < 2; ++side) {
+            const int peer = side ? s.rank + 1 : s.rank - 1;
+            if (peer < 0 || peer >= c->opt.world) continue;
+            if (is_local(c, peer)) {
+                Slab &o = *local_slab(c, peer);
+                // my ghosts from `side` are the peer's message towards me: its side (1 - side)
+                CU(cudaStreamWaitEvent(s.core.stream, o.ev_packed[kind], 0));
+                CU(cudaMemcpyPeerAsync(s.recv[kind][side], s.device, o.send[kind][1 - side], o.device, bytes,
+                                       s.core.stream));
+                CU(cudaEventRecord(s.ev_copied[kind][side], s.core.stream));
+                s.copied_pending[kind][side] = true;
+            } else {
+                if (!grouped) {
+                    NC(g_nccl.GroupStart());
+                    grouped = true;
+                }
+                NC(g_nccl.Send(s.send[kind][side], bytes, ncclChar, peer, s.comm, s.core.stream));
+                NC(g_nccl.Recv(s.recv[kind][side], bytes, ncclChar, peer, s.comm, s.core.stream));
+            }
+        }
+        if (grouped) NC(g_nccl.GroupEnd());
+    }
+    return 0;
+}
+
+// Before a slab overwrites its send buffers of `kind`: the local neighbours must have copied
+// the previous contents out.
+int wait_taken(sph_cluster *c, Slab &s, int kind) {
+    for (int side = 0; side < 2; ++side) {
+        const int peer = side ? s.rank + 1 : s.rank - 1;
+        if (peer < 0 || peer >= c->opt.world || !is_local(c, peer)) continue;
+        Slab &o = *local_slab(c, peer);
+        if (o.copied_pending[kind][1 - side]) {   // the peer copies my message from ITS side (1 - side)
+            CU(cudaStreamWaitEvent(s.core.stream, o.ev_copied[kind][1 - side], 0));
+            o.copied_pending[kind][1 - side] = false;
+        }
+    }
+    return 0;
+}
+
+MsgHeader *msg_or_null(const sph_cluster *c, const Slab &s, MsgHeader *m, int side) {
+    const int peer = side ? s.rank + 1 : s.rank - 1;
+    return (peer < 0 || peer >= c->opt.world) ? nullptr : m;
+}
+
+// Launch parameters of a slab: counts come from SlabDyn, the host only knows the capacity.
+Params launch_params(const Slab &s, int cap) {
+    Params p = *s.core.p;
+    p.n = p.n_owned = cap;
+    p.dyn = s.dyn;
+    p.cta_gap_at = p.cta_gap_len = p.cta_count = 0;
+    p.slot_begin = 0;
+    p.slot_end = cap + 2 * s.core.ghost_cap;
+    return p;
+}
+
+int enqueue_step(sph_cluster *c) {
+    const int cap = c->cap;
+    // -- build: sort, reorder, pack the boundary layers ---------------------------------------
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params p = launch_params(s, cap);
+        DeviceState &d = *s.core.d;
+        cudaStream_t st = s.core.stream;
+        if (!s.hashed) {   // after a load: keys of everything
+            launch_hash_range(p, d, 0, cap, st);   // (entries beyond n_total are never sorted)
+            s.hashed = true;
+            c->launches += 1;
+        }
+        *s.core.sorted_buf = sort_pairs_async(d.key, d.pairs[0], d.pairs[1], cap, *s.core.passes, d.sort_scratch,
+                                              s.core.sm_count, st, nullptr, &s.dyn->n_total);
+        d.sorted_pairs = d.pairs[*s.core.sorted_buf];
+        launch_reorder(p, d, *s.core.sorted_buf, cap, s.core.sm_count, st);
+        int rc = wait_taken(c, s, kHaloA);
+        if (rc) return rc;
+        launch_pack_layer(p, d, false, msg_or_null(c, s, s.send[kHaloA][0], 0), msg_or_null(c, s, s.send[kHaloA][1], 1),
+                          c->cap_g, s.dyn, st);
+        c->launches += 3 + *s.core.passes;
+    }
+    int rc = exchange(c, kHaloA);
+    if (rc) return rc;
+    // -- ghosts in, density, pack {p, a} -------------------------------------------------------
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params p = launch_params(s, cap);
+        DeviceState &d = *s.core.d;
+        cudaStream_t st = s.core.stream;
+        for (int side = 0; side < 2; ++side)
+            launch_ghost_install(p, d, msg_or_null(c, s, s.recv[kHaloA][side], side), c->cap_g, side, s.dyn, st);
+        launch_density(p, *s.core.th, d, false, st);
+        rc = wait_taken(c, s, kHaloB);
+        if (rc) return rc;
+        launch_pack_layer(p, d, true, msg_or_null(c, s, s.send[kHaloB][0], 0), msg_or_null(c, s, s.send[kHaloB][1], 1),
+                          c->cap_g, s.dyn, st);
+        c->launches += 4;
+    }
+    rc = exchange(c, kHaloB);
+    if (rc) return rc;
+    // -- ghost pressures in, force + integrate (emigrants into the migration messages) ---------
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params p = launch_params(s, cap);
+        DeviceState &d = *s.core.d;
+        cudaStream_t st = s.core.stream;
+        launch_ghost_pa(p, d, msg_or_null(c, s, s.recv[kHaloB][0], 0), msg_or_null(c, s, s.recv[kHaloB][1], 1),
+                        c->cap_g, st);
+        rc = wait_taken(c, s, kMigrate);
+        if (rc) return rc;
+        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(s.send[kMigrate][side], 0, sizeof(MsgHeader), st));
+        launch_force_integrate(p, *s.core.th, d, st);
+        c->launches += 2;
+    }
+    rc = exchange(c, kMigrate);
+    if (rc) return rc;
+    // -- immigrants appended, counts of the next step --------------------------------------------
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params p = launch_params(s, cap);
+        launch_append_immigrants(p, *s.core.d, msg_or_null(c, s, s.recv[kMigrate][0], 0),
+                                 msg_or_null(c, s, s.recv[kMigrate][1], 1), c->cap_m, s.send[kMigrate][0],
+                                 s.send[kMigrate][1], cap, s.dyn, false, s.core.stream);
+        CU(cudaMemcpyAsync(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, s.core.stream));
+        c->launches += 2;
+    }
+    c->steps_since_rebalance += 1;
+    return 0;
+}
+
+int sync_all(sph_cluster *c) {
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        CU(cudaStreamSynchronize(s.core.stream));
+        if (s.copy_stream) CU(cudaStreamSynchronize(s.copy_stream));
+        CU(cudaGetLastError());
+        s.out_pending = false;
+        s.known_total = s.dyn_host->n_total;
+        if (s.dyn_host->overflow)
+            return sph_internal_fail(SPH_E_STATE,
+                                     "slab %d: capacity exceeded (flags %u: 1 = particles, 2 = ghost layer, 4 = emigrants "
+                                     "per step); particles were lost -- raise SphClusterOptions capacities",
+                                     s.rank, s.dyn_host->overflow);
+    }
+    return 0;
+}
+
+// Kinetic energy of the owned particles (state after the last step) and the density sum of that
+// step (its live particles, per sorted slot).
+__global__ void __launch_bounds__(256)
+    k_cluster_stats(const SlabDyn *dyn, const float4 *__restrict__ cur_pos, const float4 *__restrict__ cur_vel,
+                    const float *__restrict__ rho, int slot0, double *out) {
+    double ke = 0.0, rs = 0.0;
+    const int n_total = dyn->n_total, n_prev = dyn->n_prev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += gridDim.x * blockDim.x) {
+        if (__float_as_uint(cur_pos[i].w) == 0xffffffffu) continue;   // emigrated
+        const float4 v = cur_vel[i];
+        ke += 0.5 * (double)kMass * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_prev; i += gridDim.x * blockDim.x)
+        rs += (double)rho[slot0 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ke += __shfl_xor_sync(0xffffffffu, ke, o);
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, ke);
+        atomicAdd(out + 1, rs);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sph_cluster_nccl_id(uint8_t id[SPH_NCCL_ID_BYTES]) {
+    if (!id) return sph_internal_fail(SPH_E_INVALID, "null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) <= SPH_NCCL_ID_BYTES, "ncclUniqueId grew");
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memset(id, 0, SPH_NCCL_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cluster **out) {
+    if (!st || !o || !out) return sph_internal_fail(SPH_E_INVALID, "null argument");
+    *out = nullptr;
+    if (o->world < 1 || o->local_count < 1 || o->local_count > SPH_MAX_LOCAL_SLABS || o->first_rank < 0 ||
+        o->first_rank + o->local_count > o->world)
+        return sph_internal_fail(SPH_E_INVALID, "bad slab layout: world %d, first_rank %d, local_count %d", o->world,
+                                 o->first_rank, o->local_count);
+    const int nc = (int)st->numCellsPerDim;
+    const int nz = o->nz_cells > 0 ? o->nz_cells : nc;
+    if (nz < 3 * o->world) return sph_internal_fail(SPH_E_INVALID, "%d cell layers cannot be split into %d slabs of >= 3 layers", nz, o->world);
+    sph_cluster *c = new (std::nothrow) sph_cluster();
+    if (!c) return sph_internal_fail(SPH_E_NOMEM, "out of host memory");
+    c->st = *st;
+    c->opt = *o;
+    c->nz = nz;
+    c->nc = nc;
+    const long long share = ((long long)st->numParticles + o->world - 1) / o->world;
+    c->cap = o->capacity > 0 ? o->capacity : (int)std::min<long long>(share + share / 4 + 65536, 0x7fffffff);
+    c->cap_g = o->ghost_capacity > 0 ? o->ghost_capacity : c->cap / 8 + 1024;
+    c->cap_g = (c->cap_g + 1) & ~1;
+    c->cap_m = o->emig_capacity > 0 ? o->emig_capacity : c->cap / 32 + 1024;
+    c->msg_bytes[kHaloA] = sizeof(MsgHeader) + (size_t)c->cap_g * 2 * sizeof(float4);
+    c->msg_bytes[kHaloB] = sizeof(MsgHeader) + (size_t)c->cap_g * sizeof(float2);
+    c->msg_bytes[kMigrate] = sizeof(MsgHeader) + (size_t)c->cap_m * 2 * sizeof(float4);
+    split_layers(nz, o->world, c->zlo, c->zhi);
+    c->max_layers.resize(o->world);
+    for (int r = 0; r < o->world; ++r) c->max_layers[r] = c->zhi[r] - c->zlo[r] + kSlabSpareLayers;
+    const bool need_nccl = o->local_count < o->world;
+    int rc = need_nccl ? load_nccl() : 0;
+    c->slabs.resize(o->local_count);
+    for (int i = 0; i < o->local_count && rc == 0; ++i) {
+        Slab &s = c->slabs[i];
+        s.rank = o->first_rank + i;
+        s.device = o->devices[i];
+        SphSettings ss = *st;
+        ss.numParticles = 0;
+        SphOptions so;
+        memset(&so, 0, sizeof so);
+        so.device = s.device;
+        so.key_mode = SPH_KEY_FLAT;
+        so.use_graph = 2;
+        so.capacity = c->cap;
+        so.z_cell_lo = c->zlo[s.rank];
+        so.z_cell_hi = c->zhi[s.rank];
+        so.nz_cells = nz;
+        so.ghost_capacity = c->cap_g;
+        so.emig_capacity = 1;   // the migration messages below replace the classic emigrant buffers
+        so.density_sum = o->density_sum;
+        rc = sph_create_ex(&ss, &so, &s.sim);
+        if (rc == 0) rc = sph_setup(s.sim);
+        if (rc == 0) rc = sph_internal_core(s.sim, &s.core);
+        if (rc) break;
+        s.zlo = so.z_cell_lo;
+        s.zhi = so.z_cell_hi;
+        auto fail_cuda = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) rc = sph_internal_fail((int)e, "cluster allocation failed: %s", cudaGetErrorString(e)); };
+        fail_cuda(cudaSetDevice(s.device));
+        fail_cuda(cudaMalloc(&s.dyn, sizeof(SlabDyn)));
+        fail_cuda(cudaMemset(s.dyn, 0, sizeof(SlabDyn)));
+        fail_cuda(cudaMallocHost(&s.dyn_host, sizeof(SlabDyn)));
+        if (rc == 0) memset(s.dyn_host, 0, sizeof(SlabDyn));
+        fail_cuda(cudaMalloc(&s.stats_dev, 2 * sizeof(double)));
+        for (int k = 0; k < kMsgKinds && rc == 0; ++k) {
+            for (int side = 0; side < 2 && rc == 0; ++side) {
+                rc = alloc_msg(&s.send[k][side], c->msg_bytes[k]);
+                if (rc == 0) rc = alloc_msg(&s.recv[k][side], c->msg_bytes[k]);
+                fail_cuda(cudaEventCreateWithFlags(&s.ev_copied[k][side], cudaEventDisableTiming));
+            }
+            fail_cuda(cudaEventCreateWithFlags(&s.ev_packed[k], cudaEventDisableTiming));
+        }
+        fail_cuda(cudaEventCreate(&s.ev_t0));
+        fail_cuda(cudaEventCreate(&s.ev_t1));
+        if (rc) break;
+        // the force kernel appends emigrants straight into the migration messages
+        DeviceState &d = *s.core.d;
+        for (int side = 0; side < 2; ++side) {
+            cudaFree(d.emig_pos[side]);
+            cudaFree(d.emig_vel[side]);
+            d.emig_pos[side] = reinterpret_cast<float4 *>(s.send[kMigrate][side] + 1);
+            d.emig_vel[side] = d.emig_pos[side] + c->cap_m;
+            d.emig_count[side] = &s.send[kMigrate][side]->count;
+        }
+        d.emig_capacity = c->cap_m;
+        if (need_nccl) {
+            ncclUniqueId u;
+            memcpy(&u, o->nccl_id, sizeof(u));
+            ncclResult_t r = g_nccl.CommInitRank(&s.comm, o->world, u, s.rank);
+            if (r != ncclSuccess) rc = sph_internal_fail(SPH_E_STATE, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    // peer access between the devices of local neighbours (NVLink P2P); a failure only means the
+    // copies are staged by the driver
+    for (size_t i = 0; i + 1 < c->slabs.size() && rc == 0; ++i) {
+        const int a = c->slabs[i].device, b = c->slabs[i + 1].device;
+        if (a == b) continue;
+        int ok = 0;
+        if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok) {
+            cudaSetDevice(a);
+            if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
+            cudaSetDevice(b);
+            if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
+        }
+    }
+    if (rc) {
+        sph_cluster_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void sph_cluster_destroy(sph_cluster *c) {
+    if (!c) return;
+    for (Slab &s : c->slabs) {
+        cudaSetDevice(s.device);
+        if (s.core.stream) cudaStreamSynchronize(s.core.stream);
+        if (s.copy_stream) {
+            cudaStreamSynchronize(s.copy_stream);
+            cudaStreamDestroy(s.copy_stream);
+        }
+        if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+        if (s.sim) {
+            // the emigrant pointers alias the migration messages, which are freed below
+            DeviceState *d = s.core.d;
+            if (d) {
+                for (int side = 0; side < 2; ++side) d->emig_pos[side] = d->emig_vel[side] = nullptr;
+                d->emig_count[0] = d->emig_count[1] = nullptr;
+            }
+        }
+        for (int k = 0; k < kMsgKinds; ++k) {
+            for (int side = 0; side < 2; ++side) {
+                cudaFree(s.send[k][side]);
+                cudaFree(s.recv[k][side]);
+                if (s.ev_copied[k][side]) cudaEventDestroy(s.ev_copied[k][side]);
+            }
+            if (s.ev_packed[k]) cudaEventDestroy(s.ev_packed[k]);
+        }
+        if (s.ev_t0) cudaEventDestroy(s.ev_t0);
+        if (s.ev_t1) cudaEventDestroy(s.ev_t1);
+        if (s.ev_out_ready) cudaEventDestroy(s.ev_out_ready);
+        if (s.ev_out_done) cudaEventDestroy(s.ev_out_done);
+        cudaFree(s.dyn);
+        cudaFree(s.stats_dev);
+        cudaFree(s.out_stage);
+        if (s.dyn_host) cudaFreeHost(s.dyn_host);
+        if (s.host_records) cudaFreeHost(s.host_records);
+        if (s.sim) sph_destroy(s.sim);
+    }
+    delete c;
+}
+
+int sph_cluster_load(sph_cluster *c, int li, int n, const float *pos, const float *vel, const uint32_t *ids) {
+    if (!c || li < 0 || li >= (int)c->slabs.size()) return sph_internal_fail(SPH_E_INVALID, "bad slab index");
+    Slab &s = c->slabs[li];
+    int rc = sph_slab_load(s.sim, n, pos, vel, ids);
+    if (rc) return rc;
+    CU(cudaSetDevice(s.device));
+    SlabDyn h;
+    memset(&h, 0, sizeof h);
+    h.n_total = h.n_live = n;
+    CU(cudaMemcpy(s.dyn, &h, sizeof h, cudaMemcpyHostToDevice));
+    *s.dyn_host = h;
+    s.known_total = n;
+    s.hashed = false;
+    for (int k = 0; k < kMsgKinds; ++k)
+        for (int side = 0; side < 2; ++side) {
+            CU(cudaMemset(s.send[k][side], 0, sizeof(MsgHeader)));
+            CU(cudaMemset(s.recv[k][side], 0, sizeof(MsgHeader)));
+        }
+    c->loaded = true;
+    return 0;
+}
+
+// ref: simulator.cu:430-453 -- the same particle set a single simulator starts from, split by layer
+int sph_cluster_setup(sph_cluster *c) {
+    if (!c) return sph_internal_fail(SPH_E_INVALID, "null cluster");
+    const SphSettings &st = c->st;
+    const int n = st.numParticles;
+    if (c->nz != c->nc) return sph_internal_fail(SPH_E_INVALID, "sph_cluster_setup() initialises the reference's cubic box; use sph_cluster_load() for nz_cells != numCellsPerDim");
+    std::vector<float> pos((size_t)3 * std::max(n, 1));
+    if (st.randomInit) {
+        for (int i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a) pos[3 * (size_t)i + a] = rand() / (float)RAND_MAX * (st.boxDim - 2.f) + 1.f;
+    } else {
+        const float spacing = 0.9f * st.h;
+        const int nx = (int)(floorf((st.boxDim - 2 * st.h) / spacing) + 1);
+        if ((long long)n > (long long)nx * nx * nx)
+            return sph_internal_fail(SPH_E_INVALID, "grid init: the %d^3 lattice of a boxDim=%g box cannot hold %d particles", nx, (double)st.boxDim, n);
+        int count = 0;
+        for (int x = 0; x < nx && count < n; ++x)
+            for (int y = 0; y < nx && count < n; ++y)
+                for (int z = 0; z < nx && count < n; ++z) {
+                    pos[3 * (size_t)count] = st.h + spacing * x;
+                    pos[3 * (size_t)count + 1] = st.h + spacing * y;
+                    pos[3 * (size_t)count + 2] = st.h + spacing * z;
+                    ++count;
+                }
+    }
+    for (size_t li = 0; li < c->slabs.size(); ++li) {
+        Slab &s = c->slabs[li];
+        std::vector<float> mp;
+        std::vector<uint32_t> mi;
+        for (int i = 0; i < n; ++i) {
+            int cz = (int)(pos[3 * (size_t)i + 2] / st.h);   // IEEE divide, truncate (ref: simulator.cu:69)
+            cz = std::min(std::max(cz, 0), c->nz - 1);
+            if (cz >= s.zlo && cz < s.zhi) {
+                mp.insert(mp.end(), &pos[3 * (size_t)i], &pos[3 * (size_t)i] + 3);
+                mi.push_back((uint32_t)i);
+            }
+        }
+        if ((int)mi.size() > c->cap)
+            return sph_internal_fail(SPH_E_INVALID, "slab %d would own %zu particles, capacity %d", s.rank, mi.size(), c->cap);
+        int rc = sph_cluster_load(c, (int)li, (int)mi.size(), mp.data(), nullptr, mi.data());
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int sph_cluster_sync(sph_cluster *c) {
+    if (!c) return sph_internal_fail(SPH_E_INVALID, "null cluster");
+    return sync_all(c);
+}
+
+int sph_cluster_advance(sph_cluster *c, int steps) {
+    if (!c || steps < 0) return sph_internal_fail(SPH_E_INVALID, "bad argument");
+    if (!c->loaded) return sph_internal_fail(SPH_E_STATE, "no particles: call sph_cluster_setup() or sph_cluster_load()");
+    for (int k = 0; k < steps; ++k) {
+        if (c->opt.rebalance_every > 0 && c->steps_since_rebalance >= c->opt.rebalance_every) {
+            int rc = sph_cluster_rebalance(c);
+            if (rc) return rc;
+        }
+        int rc = enqueue_step(c);
+        if (rc) return rc;
+    }
+    return sync_all(c);
+}
+
+int sph_cluster_advance_timed(sph_cluster *c, int steps, float *ms) {
+    if (!c || steps < 0 || !ms) return sph_internal_fail(SPH_E_INVALID, "bad argument");
+    if (!c->loaded) return sph_internal_fail(SPH_E_STATE, "no particles: call sph_cluster_setup() or sph_cluster_load()");
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        CU(cudaEventRecord(s.ev_t0, s.core.stream));
+    }
+    for (int k = 0; k < steps; ++k) {
+        if (c->opt.rebalance_every > 0 && c->steps_since_rebalance >= c->opt.rebalance_every) {
+            int rc = sph_cluster_rebalance(c);
+            if (rc) return rc;
+        }
+        int rc = enqueue_step(c);
+        if (rc) return rc;
+    }
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        CU(cudaEventRecord(s.ev_t1, s.core.stream));
+    }
+    int rc = sync_all(c);
+    if (rc) return rc;
+    *ms = 0.f;
+    for (Slab &s : c->slabs) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, s.ev_t0, s.ev_t1));
+        *ms = std::max(*ms, t);
+    }
+    return 0;
+}
+
+int sph_cluster_step(sph_cluster *c) {
+    if (!c) return sph_internal_fail(SPH_E_INVALID, "null cluster");
+    if (!c->loaded) return sph_internal_fail(SPH_E_STATE, "no particles: call sph_cluster_setup() or sph_cluster_load()");
+    int rc = enqueue_step(c);
+    if (rc) return rc;
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        if (!s.out_stage) {
+            CU(cudaMalloc(&s.out_stage, (size_t)c->cap * sizeof(float4)));
+            CU(cudaMallocHost(&s.host_records, (size_t)c->cap * sizeof(float4)));
+            CU(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s.ev_out_ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.ev_out_done, cudaEventDisableTiming));
+        }
+        // the host's bound on the slab's particle count: the last count it has seen plus what one
+        // step can bring in; the records beyond the true count are stale and carry no meaning
+        const int seen = std::max(s.known_total, s.dyn_host->n_total);
+        const int bound = std::min(c->cap, seen + 2 * c->cap_m);
+        if (s.out_pending) CU(cudaStreamWaitEvent(s.core.stream, s.ev_out_done, 0));   // staging buffer free again
+        CU(cudaMemcpyAsync(s.out_stage, s.core.d->cur_pos, (size_t)bound * sizeof(float4), cudaMemcpyDeviceToDevice,
+                           s.core.stream));
+        CU(cudaEventRecord(s.ev_out_ready, s.core.stream));
+        CU(cudaStreamWaitEvent(s.copy_stream, s.ev_out_ready, 0));
+        CU(cudaMemcpyAsync(s.host_records, s.out_stage, (size_t)bound * sizeof(float4), cudaMemcpyDeviceToHost,
+                           s.copy_stream));
+        CU(cudaEventRecord(s.ev_out_done, s.copy_stream));
+        s.out_pending = true;
+        s.out_count = bound;
+    }
+    return 0;
+}
+
+int sph_cluster_host_records(sph_cluster *c, int li, const float **records, int *count) {
+    if (!c || li < 0 || li >= (int)c->slabs.size() || !records || !count) return sph_internal_fail(SPH_E_INVALID, "bad argument");
+    Slab &s = c->slabs[li];
+    *records = reinterpret_cast<const float *>(s.host_records);
+    *count = std::min(s.out_count, std::max(s.dyn_host->n_total, 0));
+    return 0;
+}
+
+int sph_cluster_download(sph_cluster *c, int li, uint32_t *ids, float *pos, float *vel, int *n_out) {
+    if (!c || li < 0 || li >= (int)c->slabs.size()) return sph_internal_fail(SPH_E_INVALID, "bad slab index");
+    int rc = sync_all(c);
+    if (rc) return rc;
+    Slab &s = c->slabs[li];
+    CU(cudaSetDevice(s.device));
+    const int n = s.dyn_host->n_total;
+    std::vector<float4> hp((size_t)std::max(n, 1)), hv((size_t)std::max(n, 1));
+    if (n) {
+        CU(cudaMemcpy(hp.data(), s.core.d->cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hv.data(), s.core.d->cur_vel, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t id;
+        memcpy(&id, &hp[i].w, 4);
+        if (id == 0xffffffffu) continue;   // emigrated
+        if (ids) ids[m] = id;
+        if (pos) { pos[3 * m] = hp[i].x; pos[3 * m + 1] = hp[i].y; pos[3 * m + 2] = hp[i].z; }
+        if (vel) { vel[3 * m] = hv[i].x; vel[3 * m + 1] = hv[i].y; vel[3 * m + 2] = hv[i].z; }
+        ++m;
+    }
+    if (n_out) *n_out = m;
+    return 0;
+}
+
+int sph_cluster_positions(sph_cluster *c, float *out, int64_t n_global) {
+    if (!c || !out) return sph_internal_fail(SPH_E_INVALID, "bad argument");
+    int rc = sync_all(c);
+    if (rc) return rc;
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const int n = s.dyn_host->n_total;
+        std::vector<float4> hp((size_t)std::max(n, 1));
+        if (n) CU(cudaMemcpy(hp.data(), s.core.d->cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) {
+            uint32_t id;
+            memcpy(&id, &hp[i].w, 4);
+            if (id == 0xffffffffu) continue;
+            if ((int64_t)id >= n_global) return sph_internal_fail(SPH_E_STATE, "slab %d holds id %u >= %lld", s.rank, id, (long long)n_global);
+            out[3 * (size_t)id] = hp[i].x;
+            out[3 * (size_t)id + 1] = hp[i].y;
+            out[3 * (size_t)id + 2] = hp[i].z;
+        }
+    }
+    return 0;
+}
+
+int sph_cluster_stats(sph_cluster *c, int li, SphSlabStats *out) {
+    if (!c || li < 0 || li >= (int)c->slabs.size() || !out) return sph_internal_fail(SPH_E_INVALID, "bad argument");
+    int rc = sync_all(c);
+    if (rc) return rc;
+    Slab &s = c->slabs[li];
+    CU(cudaSetDevice(s.device));
+    memset(out, 0, sizeof *out);
+    CU(cudaMemcpy(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost));
+    const SlabDyn &h = *s.dyn_host;
+    out->rank = s.rank;
+    out->device = s.device;
+    out->z_cell_lo = s.zlo;
+    out->z_cell_hi = s.zhi;
+    out->n_owned = h.n_live;
+    out->ghosts_lo = h.g_lo;
+    out->ghosts_hi = h.g_hi;
+    out->steps = h.steps;
+    out->migrated_total = (int64_t)h.migrated;
+    out->ghosts_total = (int64_t)h.ghosts;
+    out->overflow = h.overflow;
+    out->rebalances = s.rebalances;
+    double hs[2] = {0, 0};
+    CU(cudaMemsetAsync(s.stats_dev, 0, 2 * sizeof(double), s.core.stream));
+    k_cluster_stats<<<148 * 4, 256, 0, s.core.stream>>>(s.dyn, s.core.d->cur_pos, s.core.d->cur_vel, s.core.d->rho,
+                                                        s.core.p->slot0, s.stats_dev);
+    CU(cudaMemcpyAsync(hs, s.stats_dev, sizeof hs, cudaMemcpyDeviceToHost, s.core.stream));
+    CU(cudaStreamSynchronize(s.core.stream));
+    out->kinetic_energy = hs[0];
+    out->density_sum = hs[1];
+    return 0;
+}
+
+int64_t sph_cluster_launch_count(sph_cluster *c) { return c ? c->launches : 0; }
+
+// ---- load rebalancing ---------------------------------------------------------------------------
+// Every boundary between two slabs moves by at most one layer towards the lighter slab, when that
+// reduces the difference of their particle counts.  The particles of a layer that changes owner
+// are sent through the ordinary migration messages: k_rekey_emigrate marks everything outside the
+// new range as emigrated and re-keys the rest for the new local layer numbering.
+int sph_cluster_rebalance(sph_cluster *c) {
+    if (!c) return sph_internal_fail(SPH_E_INVALID, "null cluster");
+    c->steps_since_rebalance = 0;
+    const int W = c->opt.world;
+    if (W == 1) return 0;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    // per rank: live particles and the population of its lowest / highest owned layer
+    std::vector<int> info((size_t)3 * W, 0);
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params &p = *s.core.p;
+        const uint32_t nn = (uint32_t)p.nc * p.nc;
+        uint32_t b[4];
+        const size_t at[4] = {nn, 2 * (size_t)nn, (size_t)nn * (p.ncz - 2), (size_t)nn * (p.ncz - 1)};
+        for (int i = 0; i < 4; ++i) CU(cudaMemcpy(&b[i], s.core.d->cell_start + at[i], 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost));
+        info[3 * s.rank] = s.dyn_host->n_live;
+        info[3 * s.rank + 1] = s.dyn_host->steps ? (int)(b[1] - b[0]) : 0;
+        info[3 * s.rank + 2] = s.dyn_host->steps ? (int)(b[3] - b[2]) : 0;
+    }
+    if (c->opt.local_count < W) {   // one process per GPU: all-gather the triples
+        Slab &s = c->slabs[0];
+        CU(cudaSetDevice(s.device));
+        int *dev = nullptr;
+        CU(cudaMalloc(&dev, sizeof(int) * 3 * (size_t)W));
+        CU(cudaMemcpy(dev + 3 * s.rank, &info[3 * s.rank], sizeof(int) * 3, cudaMemcpyHostToDevice));
+        NC(g_nccl.AllGather(dev + 3 * s.rank, dev, 3, ncclInt32, s.comm, s.core.stream));
+        CU(cudaStreamSynchronize(s.core.stream));
+        CU(cudaMemcpy(info.data(), dev, sizeof(int) * 3 * (size_t)W, cudaMemcpyDeviceToHost));
+        cudaFree(dev);
+    }
+    // decisions, identical on every process
+    std::vector<int> zlo = c->zlo, zhi = c->zhi;
+    bool any = false;
+    for (int r = 0; r + 1 < W; ++r) {
+        const long long a = info[3 * r], b = info[3 * (r + 1)];
+        const long long top_a = info[3 * r + 2], bottom_b = info[3 * (r + 1) + 1];
+        // move a's top layer up to b if that shrinks |a - b|, or b's bottom layer down to a; a slab
+        // keeps at least 3 layers and stays within its cell table (both known on every process)
+        if (a - b > top_a && top_a > 0 && zhi[r] - zlo[r] > 3 && zhi[r + 1] - zlo[r + 1] < c->max_layers[r + 1]) {
+            zhi[r] -= 1; zlo[r + 1] -= 1; any = true;
+        } else if (b - a > bottom_b && bottom_b > 0 && zhi[r + 1] - zlo[r + 1] > 3 && zhi[r] - zlo[r] < c->max_layers[r]) {
+            zhi[r] += 1; zlo[r + 1] += 1; any = true;
+        }
+    }
+    if (!any) return 0;
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        if (zlo[s.rank] != s.zlo || zhi[s.rank] != s.zhi) {
+            apply_range(s, zlo[s.rank], zhi[s.rank]);
+            s.rebalances += 1;
+        }
+        rc = wait_taken(c, s, kMigrate);
+        if (rc) return rc;
+        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(s.send[kMigrate][side], 0, sizeof(MsgHeader), s.core.stream));
+        Params p = launch_params(s, c->cap);
+        launch_rekey_emigrate(p, *s.core.d, s.core.stream);
+        c->launches += 1;
+    }
+    c->zlo = zlo;
+    c->zhi = zhi;
+    rc = exchange(c, kMigrate);
+    if (rc) return rc;
+    for (Slab &s : c->slabs) {
+        CU(cudaSetDevice(s.device));
+        const Params p = launch_params(s, c->cap);
+        // (rebalance = true: append behind n_total and keep the earlier dead entries counted)
+        launch_append_immigrants(p, *s.core.d, msg_or_null(c, s, s.recv[kMigrate][0], 0),
+                                 msg_or_null(c, s, s.recv[kMigrate][1], 1), c->cap_m, s.send[kMigrate][0],
+                                 s.send[kMigrate][1], c->cap, s.dyn, true, s.core.stream);
+        CU(cudaMemcpyAsync(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, s.core.stream));
+        c->launches += 2;
+    }
+    return sync_all(c);
+}
+
+}  // extern "C"

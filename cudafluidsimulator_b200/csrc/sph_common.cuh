@@ -18,6 +18,22 @@ constexpr float kPushStrength = 5.f;    // ref: simulator.cu:13 PUSH_STRENGTH
 
 enum KeyMode : int { kKeyFlat = 0, kKeyMorton = 1 };
 
+// Slab cluster (multi-GPU, csrc/sph_cluster.cu): the particle counts of a slab live in device
+// memory and never cross the host inside a step; kernels are launched over the slab's capacity and
+// read what they need from here.
+struct SlabDyn {
+    int n_total;        // entries of the cur arrays in use (live + emigrated-dead + appended immigrants)
+    int n_live;         // live particles = sorted slots [slot0, slot0 + n_live) of this step
+    int n_dead;         // entries among n_total that emigrated in the previous step (sort behind the live ones)
+    int g_lo, g_hi;     // ghost particles installed below / above the owned slots this step
+    int steps;          // steps taken (statistics)
+    unsigned overflow;  // SPH_OVF_* bits: a capacity was exceeded, particles were lost
+    int n_prev;         // live particles of the step that just finished (its rho / pa slots)
+    unsigned long long migrated;   // particles received from neighbours so far (statistics)
+    unsigned long long ghosts;     // ghost particles installed so far (statistics)
+};
+enum : unsigned { SPH_OVF_CAPACITY = 1u, SPH_OVF_GHOSTS = 2u, SPH_OVF_EMIGRANTS = 4u };
+
 // Kernel parameters, passed by value (__grid_constant__) -- no __constant__
 // symbol, so several simulators (e.g. one per slab) can coexist in a process.
 struct Params {
@@ -47,6 +63,7 @@ struct Params {
     //    flight, boundary CTAs afterwards); CTA c of the grid works on particle CTA
     //    c + (c >= cta_gap_at ? cta_gap_len : 0); cta_count = grid size, 0 = all CTAs
     int cta_gap_at, cta_gap_len, cta_count;
+    const SlabDyn *dyn;   // slab cluster: counts in device memory (n, n_owned are then upper bounds)
     // -- self-checking build (-DSPH_BOUNDS_CHECK; compute-sanitizer is closed on the GPU pool)
     int slot_begin, slot_end;   // sorted slots that hold particles this step (ghosts included)
     uint32_t *dbg;              // violation bits are OR-ed in here (see SPH_DBG_* below)
@@ -66,6 +83,9 @@ enum : uint32_t {
 #else
 #define SPH_CHECK(p, cond, bit) do { } while (0)
 #endif
+
+// Live particles of this step: a host-known launch parameter, or the slab's device-side count.
+__device__ __forceinline__ int live_count(const Params &p) { return p.dyn ? p.dyn->n_live : p.n; }
 
 // Particle CTA this thread block works on (see Params::cta_gap_at).
 __device__ __forceinline__ int particle_cta(const Params &p) {

@@ -31,8 +31,14 @@ struct DeviceState {
                                  // per particle, [CTA][word][lane] interleaved
     // slab mode: particles that left the owned z-layers during integration, per side
     float4 *emig_pos[2], *emig_vel[2];   // [0] towards lower z, [1] towards higher z
-    uint32_t *emig_count;                // 2 counters (may exceed emig_capacity: overflow)
+    uint32_t *emig_count[2];             // one counter per side (may exceed emig_capacity: overflow)
     int emig_capacity;
+};
+
+// Header of a message between neighbouring slabs (cluster mode); the payload follows it.
+struct MsgHeader {
+    uint32_t count;
+    uint32_t pad[3];
 };
 
 constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
@@ -62,5 +68,18 @@ void launch_hash_range(const Params &p, const DeviceState &d, int first, int cou
 // keys lie in [key_lo, key_hi); cell_start[k] for k in [key_lo, key_hi] is written
 void launch_ghost_prepare(const Params &p, const DeviceState &d, int first, int count,
                           uint32_t key_lo, uint32_t key_hi, cudaStream_t s);
+
+// -- slab cluster (device-resident counts; csrc/sph_cluster.cu) ---------------------------------
+void launch_pack_layer(const Params &p, const DeviceState &d, bool pa, MsgHeader *out_lo, MsgHeader *out_hi,
+                       int cap, SlabDyn *dyn, cudaStream_t s);
+void launch_ghost_install(const Params &p, const DeviceState &d, const MsgHeader *msg, int cap, int side,
+                          SlabDyn *dyn, cudaStream_t s);
+void launch_ghost_pa(const Params &p, const DeviceState &d, const MsgHeader *msg_lo, const MsgHeader *msg_hi,
+                     int cap, cudaStream_t s);
+void launch_append_immigrants(const Params &p, const DeviceState &d, const MsgHeader *from_lo,
+                              const MsgHeader *from_hi, int cap_m, const MsgHeader *sent_lo,
+                              const MsgHeader *sent_hi, int capacity, SlabDyn *dyn, bool rebalance,
+                              cudaStream_t s);
+void launch_rekey_emigrate(const Params &p, const DeviceState &d, cudaStream_t s);
 
 }  // namespace sph

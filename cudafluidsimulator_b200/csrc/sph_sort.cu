@@ -124,8 +124,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 // digits of consecutive keys are almost always equal and would otherwise
 // serialise on one shared-memory counter.
 __global__ void __launch_bounds__(kSortThreads)
-    k_histogram(const uint32_t *__restrict__ keys, int n, int passes, uint32_t *__restrict__ ghist) {
+    k_histogram(const uint32_t *__restrict__ keys, int n, const int *__restrict__ n_dev, int passes,
+                uint32_t *__restrict__ ghist) {
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
+    if (n_dev) n = *n_dev;   // count known only on the device (slab cluster): the grid covers the capacity
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kSortThreads) s_hist[i] = 0;
     __syncthreads();
 
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kSortThreads)
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     k_onesweep(const uint32_t *__restrict__ keys_in, const uint64_t *__restrict__ pairs_in,
-               uint64_t *__restrict__ pairs_out, int n, int shift,
+               uint64_t *__restrict__ pairs_out, int n, const int *__restrict__ n_dev, int shift,
                const uint32_t *__restrict__ ghist,  // 256 counts of this digit
                uint32_t *__restrict__ status,       // tiles x 256, zeroed
                uint32_t *__restrict__ ticket) {     // zeroed
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     __shared__ uint32_t s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n_dev) n = *n_dev;   // (see k_histogram) CTAs beyond the last tile leave right after their ticket
     // Tiles are handed out in launch order: a tile only ever waits on tiles with
     // a smaller ticket, which are already resident or finished.
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     const uint32_t tile = s_tile;
     TRACE(0);
     const int base = (int)tile * kSortTile;
+    if (base >= n) return;   // CTA-uniform; nobody looks back at a tile that does not exist
     const int tile_valid = min(kSortTile, n - base);
 
     // -- load -------------------------------------------------------------------
@@ -387,7 +391,8 @@ int sort_passes_for(uint32_t table_size) {
 // Enqueues: clear scratch, histogram, `passes` onesweep passes.  Returns the
 // buffer (0 or 1) holding the sorted pairs.  `launches` is incremented per kernel.
 int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, int n, int passes,
-                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks) {
+                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks,
+                     const int *n_dev) {
     const int tiles = sort_tiles(n);
     uint32_t *ghist = scratch;
     uint32_t *tickets = scratch + kMaxPasses * kRadix;
@@ -398,7 +403,7 @@ int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, i
     if (hooks) hooks->before(hooks->ctx, kSortStageHistogram);
     int hist_blocks = (n + kSortThreads * 16 - 1) / (kSortThreads * 16);
     hist_blocks = max(1, min(hist_blocks, sm_count * 8));
-    k_histogram<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, passes, ghist);
+    k_histogram<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, n_dev, passes, ghist);
     if (hooks) hooks->after(hooks->ctx, kSortStageHistogram);
 
     uint64_t *bufs[2] = {pairs0, pairs1};
@@ -407,12 +412,12 @@ int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, i
         if (hooks) hooks->before(hooks->ctx, kSortStagePass);
         uint32_t *st = status + (size_t)p * tiles * kRadix;
         if (p == 0) {
-            k_onesweep<true><<<tiles, kSortThreads, 0, stream>>>(keys, nullptr, bufs[0], n, 0, ghist,
+            k_onesweep<true><<<tiles, kSortThreads, 0, stream>>>(keys, nullptr, bufs[0], n, n_dev, 0, ghist,
                                                                st, tickets + p);
             out = 0;
         } else {
             k_onesweep<false><<<tiles, kSortThreads, 0, stream>>>(
-                nullptr, bufs[out], bufs[out ^ 1], n, 8 * p, ghist + p * kRadix, st, tickets + p);
+                nullptr, bufs[out], bufs[out ^ 1], n, n_dev, 8 * p, ghist + p * kRadix, st, tickets + p);
             out ^= 1;
         }
         if (hooks) hooks->after(hooks->ctx, kSortStagePass);

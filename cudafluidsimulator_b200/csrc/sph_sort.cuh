@@ -30,7 +30,10 @@ int sort_passes_for(uint32_t table_size); // 8-bit passes needed for keys < tabl
 // Sorts (keys[i], i) for i in [0, n) by key, stably.  Pair = key << 32 | index.
 // Enqueues a scratch clear, the histogram kernel and `passes` onesweep kernels on
 // `stream`; returns which of pairs0 / pairs1 (0 / 1) receives the sorted pairs.
+// n_dev != nullptr: the count is read from device memory by the kernels and `n` is only its
+// upper bound (grid and scratch sizes) -- the slab cluster step never brings counts to the host.
 int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, int n, int passes,
-                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks);
+                     uint32_t *scratch, int sm_count, cudaStream_t stream, SortHooks *hooks,
+                     const int *n_dev = nullptr);
 
 }  // namespace sph

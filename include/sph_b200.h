@@ -236,6 +236,87 @@ int sph_slab_download(sph_sim *sim, uint32_t *ids, float *pos, float *vel, int *
  * stream, so that NCCL transfers and kernels are ordered without extra events). */
 int sph_set_stream(sph_sim *sim, void *cuda_stream);
 
+/* --- multi-GPU: a cluster of z-slabs, one per GPU -------------------------------------------
+ * north_star: "the domain is partitioned across the 8xB200 box by a spatial slab decomposition,
+ * with per-step ghost-particle halo exchange and particle migration over NVLink via NCCL or
+ * P2P".  There is no reference equivalent (single GPU); the calls mirror the
+ * single-GPU ones above (setup / advance / step / positions).
+ *
+ * The whole per-step protocol runs inside the library and never brings a count to the host:
+ * particle counts live in device memory, every kernel is launched over the slab's capacity, and
+ * halo / migration messages are fixed-capacity buffers whose header carries the count.  Slabs
+ * driven by the same process exchange them with peer-to-peer copies (cudaMemcpyPeerAsync over
+ * NVLink), slabs of different processes with ncclSend / ncclRecv (one process per GPU under
+ * torchrun: local_count = 1).  csrc/sph_cluster.cu has the protocol. */
+typedef struct sph_cluster sph_cluster;
+#define SPH_NCCL_ID_BYTES 128
+#define SPH_MAX_LOCAL_SLABS 16
+
+typedef struct SphClusterOptions {
+    int32_t world;           /* slabs (== GPUs) of the whole job                                  */
+    int32_t first_rank;      /* global index of this process's first slab                         */
+    int32_t local_count;     /* slabs this process drives: world for a single-process run,
+                                1 with one process per GPU                                        */
+    int32_t devices[SPH_MAX_LOCAL_SLABS]; /* CUDA device of each local slab (may repeat: several
+                                slabs on one GPU, used by the tests)                              */
+    int32_t nz_cells;        /* global cell layers along z (0 = numCellsPerDim); the global box is
+                                boxDim x boxDim x nz_cells*h                                      */
+    int32_t capacity;        /* particles per slab (0 = 1.25 * numParticles / world + 65536)      */
+    int32_t ghost_capacity;  /* ghost particles per face (0 = capacity / 8)                       */
+    int32_t emig_capacity;   /* emigrants per face and step (0 = capacity / 32)                   */
+    int32_t density_sum;     /* as SphOptions.density_sum                                         */
+    int32_t rebalance_every; /* sph_cluster_advance moves the slab boundaries towards equal particle
+                                counts every this many steps (0 = static slabs)                   */
+    int32_t reserved[6];
+    uint8_t nccl_id[SPH_NCCL_ID_BYTES]; /* from sph_cluster_nccl_id() on rank 0, broadcast by the
+                                caller; only read when local_count < world                        */
+} SphClusterOptions;
+
+typedef struct SphSlabStats {
+    int32_t rank, device;
+    int32_t z_cell_lo, z_cell_hi;   /* owned global cell layers [lo, hi)                          */
+    int32_t n_owned;                /* live particles                                             */
+    int32_t ghosts_lo, ghosts_hi;   /* ghost particles of the last step                           */
+    int32_t steps;
+    int64_t migrated_total;         /* particles received from neighbours since the load          */
+    int64_t ghosts_total;           /* ghost particles installed since the load                   */
+    uint32_t overflow;              /* non-zero: a capacity was exceeded, particles were lost      */
+    int32_t rebalances;             /* boundary moves applied so far                              */
+    double kinetic_energy;          /* 0.5 m |v|^2 summed over the owned particles                */
+    double density_sum;             /* sum of the last step's densities over its live particles   */
+} SphSlabStats;
+
+/* A fresh NCCL unique id (rank 0 calls this and broadcasts the bytes by any means). */
+int sph_cluster_nccl_id(uint8_t id[SPH_NCCL_ID_BYTES]);
+int sph_cluster_create(const SphSettings *settings, const SphClusterOptions *options, sph_cluster **out);
+void sph_cluster_destroy(sph_cluster *c);
+/* The reference's initialisation (ref: simulator.cu:430-453, as sph_setup) of the whole box; every
+ * slab keeps the particles of its layers.  Ids are the single-simulator ids. */
+int sph_cluster_setup(sph_cluster *c);
+/* Explicit particle set of local slab `local_index` (host arrays; ids are global). */
+int sph_cluster_load(sph_cluster *c, int local_index, int n, const float *pos, const float *vel,
+                     const uint32_t *ids);
+/* `steps` timesteps, device-resident; one synchronisation at the end. */
+int sph_cluster_advance(sph_cluster *c, int steps);
+/* The same between CUDA events on every local slab's stream; *ms = slowest local slab. */
+int sph_cluster_advance_timed(sph_cluster *c, int steps, float *ms);
+/* One timestep, then every owned particle's record {x, y, z, id} on its way to the slab's pinned
+ * host buffer (the copy overlaps the next step; sph_cluster_sync() or the next call completes it):
+ * Simulator::simulate()'s "positions on the host after every step", per slab.  A record whose id
+ * is 0xffffffff belongs to a particle that has just left the slab. */
+int sph_cluster_step(sph_cluster *c);
+int sph_cluster_sync(sph_cluster *c);
+int sph_cluster_host_records(sph_cluster *c, int local_index, const float **records, int *count);
+/* Positions of the local slabs' particles scattered into out[3 * id ...] -- getPosition() for
+ * the ids this process holds (all of them in a single-process run). */
+int sph_cluster_positions(sph_cluster *c, float *out, int64_t n_global);
+int sph_cluster_download(sph_cluster *c, int local_index, uint32_t *ids, float *pos, float *vel, int *n);
+int sph_cluster_stats(sph_cluster *c, int local_index, SphSlabStats *out);
+/* Moves slab boundaries by at most one layer each towards equal particle counts (collective:
+ * every process of the job calls it at the same step). */
+int sph_cluster_rebalance(sph_cluster *c);
+int64_t sph_cluster_launch_count(sph_cluster *c);
+
 /* Self-checking build (nvcc -DSPH_BOUNDS_CHECK, `python -m cudafluidsimulator_b200.build
  * --checked`): every data-dependent index of the hot kernels is verified on the device and
  * violations are OR-ed into *flags (bit meanings: SPH_DBG_* in csrc/sph_common.cuh).  In the
