@@ -82,7 +82,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv:
@@ -109,6 +109,13 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
     return 6650.0, 1965.0, "fallback"
+
+
+def workload_config(name, wl):
+    """`config` of the JSON line: the same keys and values in both arms (b200 and reference)."""
+    return {"workload": name, "n": wl["n"], "boxDim": wl["boxDim"], "numCellsPerDim": wl["numCellsPerDim"],
+            "h": 0.1, "timestep": 0.01,
+            "init": "random(glibc rand seed 1)" if wl["randomInit"] else "grid lattice (dam-break column)"}
 
 
 def dist_env():
@@ -144,8 +151,7 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "particle-updates/s", "unit": "particle-updates/s",
             "n_gpus": args.gpus, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: wl[k] for k in ("n", "boxDim", "numCellsPerDim")},
-                       "init": "random(glibc rand seed 1)" if wl["randomInit"] else "grid lattice"}}
+            "config": workload_config(args.workload, wl)}
     budget = 150.0
     if REF_SO.exists():
         import torch
@@ -173,7 +179,7 @@ def run_reference(args, wl, rank, world):
                                        "(the reference has no CPU implementation); value = N*steps / "
                                        "(Grid construction + SPH update buckets of simulateAndTime)"},
             "e2e": {"value": wl["n"] * steps / wall, "unit": "particle-updates/s",
-                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": wl["n"] * 12,
                     "note": "all-in wall clock of simulateAndTime incl. its per-step D2H of N*12 B into "
                             "pageable memory and its grid reset"},
             "reference_buckets_s": {"buildGrid": b[0], "sphUpdate": b[1], "memcpy": b[2]},
@@ -195,171 +201,221 @@ def flops_per_particle(C, K):
     return (9 * C + 6 * K + 3), (9 * C + 32 * K), 30.0
 
 
-def lattice_positions(n, h, box, z_shift=0.0):
-    """The reference's grid init (ref: simulator.cu:438-453) vectorised: float32 multiply and
-    add, separately rounded, x outer / z inner; optional shift along z for replicated sub-boxes."""
-    h32, sp = np.float32(h), np.float32(0.9) * np.float32(h)
-    nx = int(np.floor((np.float32(box) - np.float32(2) * h32) / sp) + 1)
-    i = np.arange(n, dtype=np.int64)
-    ix, iy, iz = i // (nx * nx), (i // nx) % nx, i % nx
-    pos = np.empty((n, 3), np.float32)
-    pos[:, 0] = h32 + sp * ix.astype(np.float32)
-    pos[:, 1] = h32 + sp * iy.astype(np.float32)
-    pos[:, 2] = h32 + sp * iz.astype(np.float32)
-    if z_shift:
-        pos[:, 2] += np.float32(z_shift)
-    return pos
+def slosh_velocity(ids, drift, sigma):
+    """z-velocity of the multi-GPU workloads: a uniform drift plus a per-particle component that
+    depends on the particle id only (a multiplicative hash mapped to a uniform variable of
+    standard deviation sigma), so that any decomposition of the same problem starts identically.
+    It makes particles cross the slab faces in both directions from the first step on."""
+    u = ((ids.astype(np.uint64) * np.uint64(2654435761)) % np.uint64(2 ** 32)).astype(np.float64) / 2.0 ** 32
+    vel = np.zeros((len(ids), 3), np.float32)
+    vel[:, 2] = (drift + sigma * np.sqrt(3.0) * (2.0 * u - 1.0)).astype(np.float32)
+    return vel
 
 
-def run_slabs(args, wl, rank, local_rank, world):
-    """N > 1: weak scaling, one slab per GPU.  The N=1 workload (sub-box) is replicated along
-    z (the decomposition axis); the interfaces between sub-boxes are open, so every step does a
-    real ghost halo exchange (pos/vel, then pressure terms) and particle migration over NCCL."""
+def stretched_lattice(wl, world, rank_range, total=None):
+    """Global problem of the multi-GPU runs = the N=1 workload stretched `world` times along z: the
+    reference lattice (0.9h spacing from (h,h,h), x outer / z inner; ref: simulator.cu:438-453) with
+    the same number of x-planes and world x as many lattice points along z -- one continuous fluid
+    column across all slabs.  Returns what `rank_range` = (first global z cell, one past the last)
+    owns: positions, ids, and the global particle count and cell layers."""
+    h32, box = np.float32(0.1), wl["boxDim"]
+    sp = np.float32(0.9) * h32
+    nl = int(np.floor((np.float32(box) - np.float32(2) * h32) / sp) + 1)          # lattice points per box edge
+    planes = int(np.ceil(wl["n"] / (nl * nl)))                                     # x-planes of the N=1 case
+    nlz = (nl - 2) * world
+    if total:                                                                      # strong scaling: fixed global problem
+        nlz = (nl - 2) * 8
+        planes = int(np.ceil(total / (nl * nlz)))
+    zs = h32 + sp * np.arange(nlz, dtype=np.float32)
+    nz = int(np.floor(zs[-1] / h32)) + 2                                           # + wall layer
+    if rank_range is None:
+        return None, None, planes * nl * nlz, nz
+    zlo, zhi = rank_range(nz)
+    cz = (zs / h32).astype(np.int64)
+    iz = np.nonzero((cz >= zlo) & (cz < zhi))[0]
+    ix, iy = np.arange(planes, dtype=np.int64), np.arange(nl, dtype=np.int64)
+    pos = np.empty((planes, nl, len(iz), 3), np.float32)
+    pos[..., 0] = (h32 + sp * ix.astype(np.float32))[:, None, None]
+    pos[..., 1] = (h32 + sp * iy.astype(np.float32))[None, :, None]
+    pos[..., 2] = zs[iz][None, None, :]
+    pos = pos.reshape(-1, 3)
+    ids = ((ix[:, None, None] * nl + iy[None, :, None]) * nlz + iz[None, None, :]).astype(np.uint32).ravel()
+    return pos, ids, planes * nl * nlz, nz
+
+
+def cluster_parity_check(world, rank, local_rank, nccl_id_fn, gather):
+    """A reduced problem (cubic 128-cell box, a lattice block with the sloshing velocities) run
+    through the SAME multi-GPU path (world slabs, NCCL) and on one GPU; 20 steps; kinetic energy and
+    mean density must agree (SPH trajectories diverge chaotically, north_star: aggregate bound)."""
+    import cudafluidsimulator_b200 as sph
+    from cudafluidsimulator_b200.cluster import Cluster, partition, slab_ranges
+    nc, box, steps = 128, 12.8, 20
+    h32, sp = np.float32(0.1), np.float32(0.09)
+    g = np.arange(100, dtype=np.float32)
+    zs = h32 + sp * np.arange(138, dtype=np.float32)
+    x, y, z = np.meshgrid(h32 + sp * g[:40], h32 + sp * g[:60], zs, indexing="ij")
+    pos = np.stack([x.ravel(), y.ravel(), z.ravel()], 1).astype(np.float32)
+    ids = np.arange(len(pos), dtype=np.uint32)
+    vel = slosh_velocity(ids, 1.0, 1.0)
+    st = sph.Settings(numParticles=len(pos), boxDim=box, numCellsPerDim=float(nc))
+    cl = Cluster(st, world=world, rank=rank, devices=[local_rank], capacity=len(pos) // world * 2 + 65536,
+                 ghost_capacity=65536, emig_capacity=65536, nccl_id=nccl_id_fn(), rebalance_every=8)
+    mine = partition(pos, 0.1, slab_ranges(nc, world))[rank]
+    cl.load(0, pos[mine], vel[mine], ids[mine])
+    cl.advance(steps)
+    s = cl.stats(0)
+    cl.close()
+    parts = gather((s["kinetic_energy"], s["density_sum"], s["n_owned"], s["migrated_total"]))
+    if rank != 0:
+        return None
+    ke = sum(q[0] for q in parts)
+    mrho = sum(q[1] for q in parts) / len(pos)
+    one = sph.Simulator(st, device=local_rank)
+    one.setup()
+    one.set_state(pos, vel)
+    one.advance(steps)
+    ke1, mrho1 = one.get_stats()
+    one.close()
+    tol_ke, tol_rho = 1e-3, 1e-4
+    return {"problem": f"{len(pos)} particles, {nc}^3 cells, {steps} steps, z-sloshing velocities, {world} slabs vs 1 GPU",
+            "kinetic_energy": [ke, ke1], "mean_density": [mrho, mrho1],
+            "rel_diff": [abs(ke - ke1) / ke1, abs(mrho - mrho1) / mrho1], "tolerance": [tol_ke, tol_rho],
+            "particles_conserved": sum(q[2] for q in parts) == len(pos),
+            "migrated": int(sum(q[3] for q in parts)),
+            "ok": bool(abs(ke - ke1) <= tol_ke * ke1 and abs(mrho - mrho1) <= tol_rho * mrho1
+                       and sum(q[2] for q in parts) == len(pos))}
+
+
+def run_cluster(args, wl, rank, local_rank, world):
+    """N > 1: one process per GPU (torchrun), one z-slab per process; the slab protocol -- ghost
+    halo exchange (pos/vel, then pressure terms), particle migration and rebalancing -- runs inside
+    libsph_b200.so over ncclSend/ncclRecv (csrc/sph_cluster.cu).  torch.distributed (gloo) only
+    carries the NCCL id, the barriers and the statistics."""
     import torch
     import torch.distributed as dist
     import cudafluidsimulator_b200 as sph
-    from cudafluidsimulator_b200.slab import SlabBackend, SlabDriver
+    from cudafluidsimulator_b200.cluster import Cluster, nccl_id, slab_ranges
 
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from cudafluidsimulator_b200.slab import partition, slab_ranges
-    nc = int(wl["numCellsPerDim"])
-    h32, box = np.float32(0.1), wl["boxDim"]
-    st = sph.Settings(numParticles=wl["n"], randomInit=wl["randomInit"], boxDim=box,
-                      numCellsPerDim=wl["numCellsPerDim"])
-    # Global problem = the N=1 workload stretched `world` times along z:
-    #   grid  : the reference lattice (0.9h spacing from (h,h,h), x outer / z inner) with the same
-    #           number of x-planes as the N=1 case and world x as many lattice points along z --
-    #           one continuous fluid column across all slabs (real halos, real migration)
-    #   random: uniform in the stretched box interior
-    if wl["randomInit"]:
-        nz = nc * world
-        ranges = slab_ranges(nz, world)
-        rng = np.random.default_rng(1234)
-        n_glob = wl["n"] * world
-        # every rank draws the same global set and keeps its slab (cheap at 1M x world)
-        gpos = rng.uniform(1.0, box - 1.0, (n_glob, 3)).astype(np.float32)
-        gpos[:, 2] = (np.float32(1.0) + rng.uniform(0, 1, n_glob).astype(np.float32) * np.float32(box * world - 2.0))
-        mine = partition(gpos, 0.1, ranges)[rank]
-        my_pos, my_ids = gpos[mine], mine.astype(np.uint32)
-    else:
-        sp = np.float32(0.9) * h32
-        nl = int(np.floor((np.float32(box) - np.float32(2) * h32) / sp) + 1)     # 283 lattice points per box edge
-        planes = int(np.ceil(wl["n"] / (nl * nl)))                                # x-planes of the N=1 case
-        # two lattice points fewer per slab than the N=1 box: keeps (owned + 2 ghost) layers x nc^2
-        # below 2^24 keys, i.e. the same three 8-bit sort passes as on one GPU
-        nlz = (nl - 2) * world
-        if args.scaling == "strong":
-            # BASELINE.json configs[3]: a fixed global problem (default 64M particles, the dam-break
-            # slab stretched 8 box lengths along z) split over however many GPUs there are
-            nlz = (nl - 2) * 8
-            planes = int(np.ceil(args.total / (nl * nlz)))
-        zs = h32 + sp * np.arange(nlz, dtype=np.float32)
-        nz = int(np.floor(zs[-1] / h32)) + 2                                       # + wall layer
-        ranges = slab_ranges(nz, world)
-        cz = (zs / h32).astype(np.int64)
-        iz = np.nonzero((cz >= ranges[rank][0]) & (cz < ranges[rank][1]))[0]
-        ix, iy, izz = np.meshgrid(np.arange(planes), np.arange(nl), iz, indexing="ij")
-        my_pos = np.empty((ix.size, 3), np.float32)
-        my_pos[:, 0] = (h32 + sp * ix.astype(np.float32)).ravel()
-        my_pos[:, 1] = (h32 + sp * iy.astype(np.float32)).ravel()
-        my_pos[:, 2] = zs[izz.ravel()]
-        my_ids = ((ix.ravel().astype(np.int64) * nl + iy.ravel()) * nlz + izz.ravel()).astype(np.uint32)
-        n_glob = planes * nl * nlz
+    dist.init_process_group("gloo")
+
+    def fresh_id():
+        box = [nccl_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    total = args.total if args.scaling == "strong" else None
+    rr = lambda nz: slab_ranges(nz, world)[rank]
+    my_pos, my_ids, n_glob, nz = stretched_lattice(wl, world, rr, total)
+    my_vel = slosh_velocity(my_ids, args.drift, args.sigma)
     n = len(my_ids)
-    zlo, zhi = ranges[rank]
+    n_max = max(gather(n))
+    st = sph.Settings(numParticles=n_glob if n_glob < 2 ** 31 else 2 ** 31 - 1, randomInit=False,
+                      boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"])
+    layer = n_max // max(1, (nz // world))            # particles per cell layer
+    caps = dict(capacity=int(n_max * 1.15) + 65536, ghost_capacity=2 * layer + 16384, emig_capacity=layer + 16384)
 
     def make():
-        b = SlabBackend(st, zlo, zhi, nz, capacity=int(n * 1.2) + 4096, device=local_rank,
-                        ghost_capacity=int(n * 0.1) + 4096, emig_capacity=int(n * 0.05) + 4096)
-        b.load(my_pos, np.zeros_like(my_pos), my_ids)
-        return b, SlabDriver(b, rank, world, overlap=not args.no_overlap)
+        cl = Cluster(st, world=world, rank=rank, devices=[local_rank], nz_cells=nz, nccl_id=fresh_id(),
+                     rebalance_every=args.rebalance_every, **caps)
+        cl.load(0, my_pos, my_vel, my_ids)
+        return cl
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        local_ms = e0.elapsed_time(e1)
-        timed.local_ms = local_ms
-        t = torch.tensor([local_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # -- device-resident timed region ---------------------------------------------------
-    b, drv = make()
-    for _ in range(args.warmup):
-        drv.step()
-    l0 = b.launch_count
+    cl = make()
+    cl.advance(args.warmup)
+    start = gather(cl.stats(0))
+    l0 = cl.launch_count
+    barrier()
     with ClockSampler(local_rank) as clocks:
-        ms = timed(drv.step, args.steps)
-    launches = b.launch_count - l0
-    if drv.host_ms is not None and rank == 0:   # SPH_SLAB_TRACE=1: host time per protocol phase
-        tot = args.steps + args.warmup
-        print("host ms/step by phase (rank 0): " +
-              ", ".join(f"{k} {v / tot:.3f}" for k, v in drv.host_ms.items()), file=sys.stderr)
-    per_rank = [None] * world
-    dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": timed.local_ms / args.steps, **drv.last,
-                                      **{k: v for k, v in drv.stats.items()}})
-    b.close()
+        local_ms = cl.advance_timed(args.steps)     # CUDA events on the slab's stream, sync at the end
+        barrier()
+    launches = cl.launch_count - l0
+    ms = max(gather(local_ms))
+    end = gather({**cl.stats(0), "ms_per_step": local_ms / args.steps})
+    cl.close()
 
-    # -- e2e: every step also copies the owned particles' positions to pinned host memory --
-    b, drv = make()
-    host = torch.empty((b.capacity, 3), dtype=torch.float32).pin_memory()     # xyz, as the reference's float3
-    stage = torch.empty((b.capacity, 3), dtype=torch.float32, device=b.device)
-    copy_stream = torch.cuda.Stream()
-    copy_done = torch.cuda.Event()
-    copy_done.record()
-
-    def step_e2e():
-        # every step's owned positions reach pinned host memory; the PCIe copy of step k runs on a
-        # side stream from a device staging copy while step k+1 computes
-        drv.step()
-        k = drv.last["n_owned"]
-        copy_done.synchronize()                  # staging buffer free again
-        stage[:k].copy_(b.cur_pos[:k, :3])       # drop the id word: 12 B per particle cross PCIe
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            host[:k].copy_(stage[:k], non_blocking=True)
-            copy_done.record()
+    # -- e2e: every step's owned particle records {x, y, z, id} reach pinned host memory ----
+    cl = make()
     for _ in range(args.warmup):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-    b.close()
+        cl.step()
+    cl.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cl.step()
+    cl.sync()
+    barrier()
+    e2e_s = max(gather(time.perf_counter() - t0))
+    rec = cl.host_records(0)
+    live = rec[:, 3].view(np.uint32) != 0xFFFFFFFF
+    rec_counts = gather((int(len(rec)), int(live.sum())))
+    cl.close()
 
+    # -- untimed: imbalance over the run (a third pass, so that the timed regions have no sync inside)
+    timeline = None
+    if args.timeline:
+        cl = make()
+        cl.advance(args.warmup)
+        timeline = []
+        chunks = 4
+        for k in range(chunks + 1):
+            owned = [q["n_owned"] for q in gather(cl.stats(0))]
+            timeline.append({"step": args.warmup + k * (args.steps // chunks),
+                             "imbalance_max_over_mean": round(max(owned) / (sum(owned) / world), 5)})
+            if k < chunks:
+                cl.advance(args.steps // chunks)
+        cl.close()
+
+    parity = cluster_parity_check(world, rank, local_rank, fresh_id, gather) if not args.no_parity else None
     if rank == 0:
-        owned = [r["n_owned"] for r in per_rank]
+        owned = [r["n_owned"] for r in end]
         line = {
             "metric": "particle-updates/s", "value": n_glob * args.steps / (ms * 1e-3),
             "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "n_per_gpu": n_glob // world, "n_total": n_glob, "boxDim": wl["boxDim"],
-                       "numCellsPerDim": wl["numCellsPerDim"], "global_cells_z": nz,
-                       "parallelism": f"{world} z-slabs, one per GPU: ghost halo exchange (pos/vel, then pressure "
-                                      "terms) + particle migration per step over NCCL send/recv",
-                       "init": "N=1 workload stretched along z: one continuous fluid body across all slabs",
-                       "l2": f"state evolves step to step; working set {n * 124 / 1e6:.0f} MB per GPU vs 126 MB L2"},
+            "config": {"workload": args.workload, "n": wl["n"], "boxDim": wl["boxDim"],
+                       "numCellsPerDim": wl["numCellsPerDim"], "h": 0.1, "timestep": 0.01,
+                       "init": "grid lattice (dam-break column)"},
+            "run": {"n_per_gpu": n_glob // world, "n_total": n_glob, "global_cells_z": nz,
+                    "init": "N=1 workload stretched along z: one continuous fluid body across all slabs; z-velocity "
+                            f"= drift {args.drift} + id-hashed uniform component of std {args.sigma} (slab faces are "
+                            "crossed in both directions from the first step)",
+                    "parallelism": f"{world} z-slabs, one process per GPU; ghost halo exchange (pos/vel, then pressure "
+                                   "terms) + particle migration per step inside libsph_b200.so over ncclSend/ncclRecv, "
+                                   "counts device-resident (no host round trip inside a step); slab boundaries "
+                                   f"rebalanced every {args.rebalance_every} steps",
+                    "l2": f"state evolves step to step; working set {n * 124 / 1e6:.0f} MB per GPU vs 126 MB L2"},
             "clocks": clocks.summary(),
-            "e2e": {"value": n_glob * args.steps / (e2e_ms * 1e-3), "unit": "particle-updates/s",
-                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": n_glob * 12,
-                    "api": "SlabDriver.step() + per-step D2H of every owned particle's position record into pinned host "
-                           "memory (copy of step k overlaps the computation of step k+1)"},
+            "e2e": {"value": n_glob * args.steps / e2e_s, "unit": "particle-updates/s",
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(sum(c[0] for c in rec_counts)) * 16,
+                    "api": "sph_cluster_step(): one step, then every owned particle's record {x, y, z, id} from the "
+                           "slab's GPU into that slab's pinned host buffer (16 B per particle; the copy of step k "
+                           "overlaps step k+1; all K copies complete inside the timed region); "
+                           "sph_cluster_positions() is the id-ordered getPosition() on demand",
+                    "records_last_step": [c[1] for c in rec_counts]},
             "gpu_launches": int(launches) * world,
-            "load_balance": {"owned_per_rank": owned, "imbalance_max_over_mean": max(owned) / (sum(owned) / world),
-                             "ghosts_last_step": [r["ghosts"] for r in per_rank],
-                             "ms_per_step_per_rank": [round(r["ms_per_step"], 4) for r in per_rank],
-                             "migrated_total": [r["migrated_particles"] for r in per_rank]},
+            "load_balance": {"owned_per_rank_start": [r["n_owned"] for r in start], "owned_per_rank_end": owned,
+                             "imbalance_max_over_mean_start": max(r["n_owned"] for r in start) / (sum(r["n_owned"] for r in start) / world),
+                             "imbalance_max_over_mean": max(owned) / (sum(owned) / world),
+                             "layers_per_rank_end": [[r["z_cell_lo"], r["z_cell_hi"]] for r in end],
+                             "rebalances_per_rank": [r["rebalances"] for r in end],
+                             "ghosts_last_step": [r["ghosts_lo"] + r["ghosts_hi"] for r in end],
+                             "ms_per_step_per_rank": [round(r["ms_per_step"], 4) for r in end],
+                             "migrated_total": [int(r["migrated_total"]) for r in end],
+                             "timeline": timeline},
+            "parity_check": parity,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
@@ -368,7 +424,7 @@ def run_slabs(args, wl, rank, local_rank, world):
 
 def run_ours(args, wl, rank, local_rank, world):
     if world > 1:
-        return run_slabs(args, wl, rank, local_rank, world)
+        return run_cluster(args, wl, rank, local_rank, world)
 
     import torch
     import cudafluidsimulator_b200 as sph
@@ -413,6 +469,8 @@ def run_ours(args, wl, rank, local_rank, world):
     # -- stage times + neighbour statistics for the rooflines (state after the timed region)
     K, C = sim.get_neighbor_counts()
     meanK, meanC = float(K.mean()), float(C.mean())
+    table_size = len(sim.get_cell_start()) - 1
+    sort_passes = (max(1, int(table_size - 1).bit_length()) + 7) // 8
     prof_steps = max(3, min(10, args.steps))
     sim.profile_enable(True)
     sim.profile_read(reset=True)
@@ -445,13 +503,13 @@ def run_ours(args, wl, rank, local_rank, world):
     hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
     clk = clocks.summary()
     f_den, f_force, f_int = flops_per_particle(meanC, meanK)
-    passes = 3
+    passes = sort_passes          # 8-bit onesweep passes the library runs for this key range
     bytes_stage = {  # algorithmic bytes per particle
         "hash": 20, "histogram": 4, "sort_passes": 4 + 8 + 16 * (passes - 1),
         "reorder_cellstart": 8 + 32 + 32 + 12 + 4 * (wl["numCellsPerDim"] ** 3) / n,
         "density": 16 + 12 + 8, "force_integrate": 16 + 16 + 8 + 4 + 8 + 16 + 16 + 4 + 12,
     }
-    ncu_kernel = {"density": "k_density_flat<0", "force_integrate": "k_force_integrate_flat",
+    ncu_kernel = {"density": "k_density_flat", "force_integrate": "k_force_integrate_flat",
                   "reorder_cellstart": "k_reorder", "sort_passes": "k_onesweep<0>", "histogram": "k_histogram"}
 
     def kernel_traffic(stage):   # DRAM bytes per launch of that stage's kernel from the committed ncu capture
@@ -461,9 +519,13 @@ def run_ours(args, wl, rank, local_rank, world):
             if name.startswith(ncu_kernel[stage]):
                 return b
         return None
+    # DRAM bytes per launch from the committed ncu --set full captures of the same workload; two
+    # states are on file (lattice: up to ~step 40; floor pile-up: around step 100) and the one that
+    # matches the state of the timed kernels is used
     traffic = None
-    tfile = ROOT / "profiles" / "r01_traffic.json"
-    if tfile.exists() and args.workload == "16m_grid":
+    state_step = args.warmup + args.steps
+    tfile = ROOT / "profiles" / ("r02_traffic_early.json" if state_step <= 40 else "r02_traffic_late.json")
+    if tfile.exists() and args.workload == "16m_grid" and args.key == "flat":
         traffic = json.loads(tfile.read_text())
     flops_stage = {"density": f_den, "force_integrate": f_force + f_int}
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
@@ -504,12 +566,12 @@ def run_ours(args, wl, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "n_per_gpu": n, "boxDim": wl["boxDim"],
-                   "numCellsPerDim": wl["numCellsPerDim"], "h": 0.1, "timestep": 0.01,
-                   "init": "random(glibc rand seed 1)" if wl["randomInit"] else "grid lattice (dam-break column)",
-                   "key": args.key, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2": "each step consumes the previous step's output (no repeated input); "
-                         f"working set {n * 108 / 1e6:.0f} MB vs 126 MB L2"},
+        "config": workload_config(args.workload, wl),
+        "run": {"key": args.key, "parallelism": "single GPU", "sort_passes": sort_passes,
+                "state": f"steps {args.warmup + 1}..{args.warmup + args.steps} from the initial condition",
+                "density_sum": "factored (library default)",
+                "l2": "each step consumes the previous step's output (no repeated input); "
+                      f"working set {n * 108 / 1e6:.0f} MB vs 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": world * n * args.steps / e2e_s, "unit": "particle-updates/s",
                 "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": 0,
@@ -585,17 +647,24 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="16m_grid", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS),
+                    help="default: 16m_grid on one GPU (BASELINE configs[2]); 32m_grid per GPU on several "
+                         "(BASELINE configs[4], the north_star weak-scaling point)")
     ap.add_argument("--key", default="flat", choices=["flat", "morton"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
     ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N > 1: halo exchanges and count round trips after, not under, the interior CTAs (A/B switch)")
+    ap.add_argument("--drift", type=float, default=1.0, help="N > 1: uniform z-velocity of the fluid column")
+    ap.add_argument("--sigma", type=float, default=1.0, help="N > 1: std of the per-particle z-velocity component")
+    ap.add_argument("--rebalance-every", type=int, default=16, help="N > 1: steps between slab boundary moves (0 = static)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the reduced-problem parity check")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: extra untimed pass reporting imbalance over the run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, local_rank, world = dist_env()
+    if args.workload is None:
+        args.workload = "16m_grid" if world == 1 else "32m_grid"   # both arms
     wl = WORKLOADS[args.workload]
     if args.compare_variants:
         if rank == 0:

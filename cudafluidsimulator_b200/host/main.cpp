@@ -6,6 +6,8 @@
 // displayTimes().  Additive flags (reference behaviour when absent):
 //   -b <boxDim>  -c <cellsPerDim>   scale the domain beyond the hard-coded 10 / 100 box
 //                                   (ref: main.cpp:62-63), needed above 109^3 particles
+//   -g <gpus>                       split the box into z-slabs over this many GPUs (one process, peer-to-peer
+//                                   halo exchange and migration inside the library; Simulator picks it up)
 //   -k <flat|morton>                cell-key form of the sort
 //   -s <steps>                      iterations in time mode (default 100, main.cpp:69)
 //   -f <frames>                     frames to run in headless free mode (default 600)
@@ -56,6 +58,7 @@ void usage() {
         "  -m  <free/time>        Execution mode: free or timed",
         "  -b  <BOX_DIM>          (extension) box edge length, default 10",
         "  -c  <CELLS_PER_DIM>    (extension) grid cells per dimension, default 100",
+        "  -g  <GPUS>             (extension) z-slab decomposition over this many GPUs, default 1",
         "  -k  <flat/morton>      (extension) cell key used by the sort, default flat",
         "  -s  <STEPS>            (extension) timed iterations, default 100",
         "  -l/-d <FILE>           (extension) load initial / dump final state",
@@ -79,7 +82,7 @@ bool choice(char flag, const std::string &value, const char *yes, const char *no
 
 // returns -1 to continue, otherwise the exit status
 int parse(int argc, char **argv, Options &o) {
-    for (int c; (c = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:o:?")) != -1;) {
+    for (int c; (c = getopt(argc, argv, "n:i:m:b:c:k:s:f:l:d:o:g:?")) != -1;) {
         const std::string v = optarg ? optarg : "";
         bool morton = false;
         switch (c) {
@@ -90,6 +93,7 @@ int parse(int argc, char **argv, Options &o) {
             if (!choice('k', v, "morton", "flat", morton)) return 1;
             setenv("SPH_KEY_MODE", morton ? "morton" : "flat", 1);
             break;
+        case 'g': setenv("SPH_GPUS", v.c_str(), 1); break;
         case 'b': o.box = std::stof(v); break;
         case 'c': o.cells = (float)std::stoi(v); break;
         case 's': o.steps = std::stoi(v); break;
@@ -170,6 +174,10 @@ int main(int argc, char **argv) {
     Simulator *simulator = new Simulator(&settings);
     simulator->setup();
     if (simulator->status() != 0) return 2;  // the reference would carry on silently
+    if ((!o.load.empty() || !o.dump.empty()) && !simulator->handle()) {
+        fprintf(stderr, "sph: -l / -d need the single-GPU simulator (drop -g)\n");
+        return 2;
+    }
     if (!o.load.empty()) {
         std::vector<float> pos, vel;
         if (!load_state(o.load, o.particles, pos, vel) ||

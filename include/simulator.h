@@ -58,7 +58,8 @@ struct Settings {
     float timestep;
 };
 
-struct sph_sim;  // opaque handle of the C ABI (include/sph_b200.h)
+struct sph_sim;      // opaque handles of the C ABI (include/sph_b200.h)
+struct sph_cluster;
 
 class Simulator {
   public:
@@ -77,11 +78,16 @@ class Simulator {
     // error reporting at all, so ignoring this reproduces its behaviour
     int status() const { return lastStatus; }
     // additive: the C-ABI handle, for callers that want the extra entry points of sph_b200.h
-    // (state I/O, parity hooks)
+    // (state I/O, parity hooks); null when the simulator runs on several GPUs
     sph_sim *handle() const { return impl; }
+    // additive: with SPH_GPUS=N (./sph -g N) the box is split into N z-slabs, one per GPU, behind
+    // the same five methods; this is the handle of that cluster (sph_cluster_* of sph_b200.h)
+    sph_cluster *clusterHandle() const { return cluster; }
 
   private:
     sph_sim *impl;
+    sph_cluster *cluster = nullptr;
+    float *clusterPositions = nullptr;   // getPosition() buffer of the multi-GPU path
     int lastStatus = 0;
     void note(int rc, const char *what);
 };

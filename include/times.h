@@ -18,17 +18,20 @@ struct Times {
 };
 
 inline void displayTimes(Times *times) {
-    const double per = times->iters ? 1.0 / times->iters : 0.0;
+    // per-frame values are quotients, as in the reference (ref: times.h:13-15)
+    const double avgBuildGrid = times->iters ? times->buildGrid / times->iters : 0.0;
+    const double avgSphUpdate = times->iters ? times->sphUpdate / times->iters : 0.0;
+    const double avgMemcpy = times->iters ? times->memcpy / times->iters : 0.0;
     char line[5][96];
     // column widths of the reference's iomanip sequence (ref: times.h:19-35)
     std::snprintf(line[0], sizeof line[0], "%-12s%18s%12s", "Operation", "Per frame", "Total");
     std::snprintf(line[1], sizeof line[1], "%s", "---------------------------------------------");
     std::snprintf(line[2], sizeof line[2], "%-11s%11.5f%15.5f", "Grid construction",
-                  times->buildGrid * per, times->buildGrid);
+                  avgBuildGrid, times->buildGrid);
     std::snprintf(line[3], sizeof line[3], "%-12s%16.5f%15.5f", "SPH update",
-                  times->sphUpdate * per, times->sphUpdate);
+                  avgSphUpdate, times->sphUpdate);
     std::snprintf(line[4], sizeof line[4], "%-12s%15.5f%15.5f", "Data transfer",
-                  times->memcpy * per, times->memcpy);
+                  avgMemcpy, times->memcpy);
     std::cout.flush();
     for (auto &l : line) std::printf("%s\n", l);
     std::fflush(stdout);
