@@ -84,8 +84,9 @@ class ClockSampler:
                 pass
             self._stop.wait(0.002)
 
-    def __enter__(self):
+    def __enter__(self):   # may be entered several times: samples of all timed regions are pooled
         if self.nv:
+            self._stop.clear()
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
         return self
@@ -94,6 +95,7 @@ class ClockSampler:
         self._stop.set()
         if self._thr:
             self._thr.join()
+            self._thr = None
 
     def summary(self):
         if not self.nv or not self.samples:
@@ -201,14 +203,20 @@ def flops_per_particle(C, K):
     return (9 * C + 6 * K + 3), (9 * C + 32 * K), 30.0
 
 
-def slosh_velocity(ids, drift, sigma):
-    """z-velocity of the multi-GPU workloads: a uniform drift plus a per-particle component that
-    depends on the particle id only (a multiplicative hash mapped to a uniform variable of
-    standard deviation sigma), so that any decomposition of the same problem starts identically.
-    It makes particles cross the slab faces in both directions from the first step on."""
-    u = ((ids.astype(np.uint64) * np.uint64(2654435761)) % np.uint64(2 ** 32)).astype(np.float64) / 2.0 ** 32
+def slosh_velocity(pos, ids, drift, sigma, y_mid):
+    """z-velocity of the multi-GPU workloads: two counter-flowing streams.  The upper half of the
+    fluid column (y >= y_mid) drifts towards +z, the lower half towards -z, each as a rigid block, so
+    EVERY slab face is crossed in both directions from the first steps on (every rank receives
+    migrants) while the lattice structure inside a stream -- the per-particle work of the N=1
+    workload -- is preserved; the streams shear past each other at mid-height and pile up against
+    the two end walls.  sigma adds a per-particle component that depends on the particle id only (a
+    multiplicative hash mapped to a uniform variable of that standard deviation)."""
     vel = np.zeros((len(ids), 3), np.float32)
-    vel[:, 2] = (drift + sigma * np.sqrt(3.0) * (2.0 * u - 1.0)).astype(np.float32)
+    vz = np.where(pos[:, 1] >= np.float32(y_mid), drift, -drift).astype(np.float64)
+    if sigma:
+        u = ((ids.astype(np.uint64) * np.uint64(2654435761)) % np.uint64(2 ** 32)).astype(np.float64) / 2.0 ** 32
+        vz = vz + sigma * np.sqrt(3.0) * (2.0 * u - 1.0)
+    vel[:, 2] = vz.astype(np.float32)
     return vel
 
 
@@ -256,7 +264,7 @@ def cluster_parity_check(world, rank, local_rank, nccl_id_fn, gather):
     x, y, z = np.meshgrid(h32 + sp * g[:40], h32 + sp * g[:60], zs, indexing="ij")
     pos = np.stack([x.ravel(), y.ravel(), z.ravel()], 1).astype(np.float32)
     ids = np.arange(len(pos), dtype=np.uint32)
-    vel = slosh_velocity(ids, 1.0, 1.0)
+    vel = slosh_velocity(pos, ids, 1.0, 0.5, 2.8)
     st = sph.Settings(numParticles=len(pos), boxDim=box, numCellsPerDim=float(nc))
     cl = Cluster(st, world=world, rank=rank, devices=[local_rank], capacity=len(pos) // world * 2 + 65536,
                  ghost_capacity=65536, emig_capacity=65536, nccl_id=nccl_id_fn(), rebalance_every=8)
@@ -286,6 +294,11 @@ def cluster_parity_check(world, rank, local_rank, nccl_id_fn, gather):
                        and sum(q[2] for q in parts) == len(pos))}
 
 
+def trace(msg):
+    if os.environ.get("SPH_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', 0)} +{time.perf_counter():.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def run_cluster(args, wl, rank, local_rank, world):
     """N > 1: one process per GPU (torchrun), one z-slab per process; the slab protocol -- ghost
     halo exchange (pos/vel, then pressure terms), particle migration and rebalancing -- runs inside
@@ -312,13 +325,15 @@ def run_cluster(args, wl, rank, local_rank, world):
     total = args.total if args.scaling == "strong" else None
     rr = lambda nz: slab_ranges(nz, world)[rank]
     my_pos, my_ids, n_glob, nz = stretched_lattice(wl, world, rr, total)
-    my_vel = slosh_velocity(my_ids, args.drift, args.sigma)
+    y_mid = 0.5 * wl["boxDim"]
+    my_vel = slosh_velocity(my_pos, my_ids, args.drift, args.sigma, y_mid)
     n = len(my_ids)
     n_max = max(gather(n))
     st = sph.Settings(numParticles=n_glob if n_glob < 2 ** 31 else 2 ** 31 - 1, randomInit=False,
                       boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"])
-    layer = n_max // max(1, (nz // world))            # particles per cell layer
-    caps = dict(capacity=int(n_max * 1.15) + 65536, ghost_capacity=2 * layer + 16384, emig_capacity=layer + 16384)
+    # a cell layer (0.1) holds one or two lattice planes (0.09 apart); the capacities leave room for more
+    plane = int(np.ceil(n_max / max(1.0, (0.1 * nz / world) / 0.09)))
+    caps = dict(capacity=int(n_max * 1.15) + 65536, ghost_capacity=5 * plane + 16384, emig_capacity=3 * plane + 16384)
 
     def make():
         cl = Cluster(st, world=world, rank=rank, devices=[local_rank], nz_cells=nz, nccl_id=fresh_id(),
@@ -330,9 +345,31 @@ def run_cluster(args, wl, rank, local_rank, world):
         dist.barrier()
         torch.cuda.synchronize()
 
+    # -- the same per-GPU problem on ONE GPU (one slab, no neighbours): the weak-scaling reference --
+    n1 = None
+    trace(f"problem built: {n} particles, nz {nz}, caps {caps}")
+    if rank == 0 and args.scaling == "weak" and not args.no_n1:
+        p1, i1, n1_glob, nz1 = stretched_lattice(wl, 1, lambda nzz: (0, nzz), None)
+        # (16 cell layers of headroom at either end: the two streams never reach a wall, i.e. the
+        # undisturbed per-particle work -- the conservative reference)
+        p1[:, 2] += np.float32(1.6)
+        c1 = Cluster(st, world=1, rank=0, devices=[local_rank], nz_cells=nz1 + 32, capacity=int(len(i1) * 1.05) + 65536,
+                     ghost_capacity=1024, emig_capacity=1024)
+        c1.load(0, p1, slosh_velocity(p1, i1, args.drift, args.sigma, y_mid), i1)
+        trace("n1 loaded")
+        c1.advance(args.warmup)
+        trace("n1 warm")
+        n1 = {"particles": int(n1_glob), "ms_per_step": c1.advance_timed(args.steps) / args.steps}
+        c1.close()
+        del p1, i1
+    dist.barrier()
+    trace("n1 done")
+
     # -- device-resident timed region ---------------------------------------------------
     cl = make()
+    trace("cluster loaded")
     cl.advance(args.warmup)
+    trace("warm")
     start = gather(cl.stats(0))
     l0 = cl.launch_count
     barrier()
@@ -341,6 +378,7 @@ def run_cluster(args, wl, rank, local_rank, world):
         barrier()
     launches = cl.launch_count - l0
     ms = max(gather(local_ms))
+    trace(f"timed: {local_ms / args.steps:.3f} ms/step")
     end = gather({**cl.stats(0), "ms_per_step": local_ms / args.steps})
     cl.close()
 
@@ -350,12 +388,14 @@ def run_cluster(args, wl, rank, local_rank, world):
         cl.step()
     cl.sync()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cl.step()
-    cl.sync()
-    barrier()
-    e2e_s = max(gather(time.perf_counter() - t0))
+    with clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cl.step()
+        cl.sync()
+        barrier()
+        e2e_s = max(gather(time.perf_counter() - t0))
+    trace("e2e done")
     rec = cl.host_records(0)
     live = rec[:, 3].view(np.uint32) != 0xFFFFFFFF
     rec_counts = gather((int(len(rec)), int(live.sum())))
@@ -388,9 +428,10 @@ def run_cluster(args, wl, rank, local_rank, world):
                        "numCellsPerDim": wl["numCellsPerDim"], "h": 0.1, "timestep": 0.01,
                        "init": "grid lattice (dam-break column)"},
             "run": {"n_per_gpu": n_glob // world, "n_total": n_glob, "global_cells_z": nz,
-                    "init": "N=1 workload stretched along z: one continuous fluid body across all slabs; z-velocity "
-                            f"= drift {args.drift} + id-hashed uniform component of std {args.sigma} (slab faces are "
-                            "crossed in both directions from the first step)",
+                    "init": "N=1 workload stretched along z: one continuous fluid body across all slabs; its upper half "
+                            f"streams towards +z and its lower half towards -z at {args.drift} (rigid blocks), plus an "
+                            f"id-hashed uniform z-component of std {args.sigma}: every slab face is crossed in both "
+                            "directions from the first steps on",
                     "parallelism": f"{world} z-slabs, one process per GPU; ghost halo exchange (pos/vel, then pressure "
                                    "terms) + particle migration per step inside libsph_b200.so over ncclSend/ncclRecv, "
                                    "counts device-resident (no host round trip inside a step); slab boundaries "
@@ -416,6 +457,11 @@ def run_cluster(args, wl, rank, local_rank, world):
                              "migrated_total": [int(r["migrated_total"]) for r in end],
                              "timeline": timeline},
             "parity_check": parity,
+            "weak_scaling_reference": None if n1 is None else {
+                **n1, "updates_per_s": n1["particles"] / (n1["ms_per_step"] * 1e-3),
+                "what": "the same per-GPU problem (one band of the column) on one GPU through the same library "
+                        "path, timed in this run on rank 0's GPU before the multi-GPU run",
+                "efficiency": (n_glob * args.steps / (ms * 1e-3)) / (world * n1["particles"] / (n1["ms_per_step"] * 1e-3))},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
@@ -469,7 +515,7 @@ def run_ours(args, wl, rank, local_rank, world):
     # -- stage times + neighbour statistics for the rooflines (state after the timed region)
     K, C = sim.get_neighbor_counts()
     meanK, meanC = float(K.mean()), float(C.mean())
-    table_size = len(sim.get_cell_start()) - 1
+    table_size = sim.table_size
     sort_passes = (max(1, int(table_size - 1).bit_length()) + 7) // 8
     prof_steps = max(3, min(10, args.steps))
     sim.profile_enable(True)
@@ -488,11 +534,12 @@ def run_ours(args, wl, rank, local_rank, world):
         for _ in range(args.warmup):
             sim.simulate()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            sim.simulate()
-        barrier()
-        dt = time.perf_counter() - t0
+        with clocks:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                sim.simulate()
+            barrier()
+            dt = time.perf_counter() - t0
         chk = float(sim.getPosition()[:: max(1, n // 1000)].sum())
         sim.close()
         return dt, chk
@@ -655,8 +702,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
     ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")
-    ap.add_argument("--drift", type=float, default=1.0, help="N > 1: uniform z-velocity of the fluid column")
-    ap.add_argument("--sigma", type=float, default=1.0, help="N > 1: std of the per-particle z-velocity component")
+    ap.add_argument("--drift", type=float, default=1.0, help="N > 1: z-speed of the two counter-flowing halves of the fluid column")
+    ap.add_argument("--sigma", type=float, default=0.0, help="N > 1: std of the per-particle z-velocity component")
+    ap.add_argument("--no-n1", action="store_true", help="N > 1: skip the one-GPU run of the same per-GPU problem")
     ap.add_argument("--rebalance-every", type=int, default=16, help="N > 1: steps between slab boundary moves (0 = static)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the reduced-problem parity check")
     ap.add_argument("--timeline", action="store_true", help="N > 1: extra untimed pass reporting imbalance over the run")

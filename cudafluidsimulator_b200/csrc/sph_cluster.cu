@@ -56,7 +56,6 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -80,7 +79,6 @@ int load_nccl() {
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
-    SYM(AllGather, "ncclAllGather");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -124,6 +122,7 @@ struct Slab {
     int known_total = 0;           // host-side bound on n_total
     int rebalances = 0;
     double *stats_dev = nullptr;   // 2 doubles
+    int *info_dev = nullptr;       // 3 x 8 ints: rebalancing numbers of this slab / from below / from above
     bool hashed = false;
 };
 
@@ -443,6 +442,7 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
         fail_cuda(cudaMallocHost(&s.dyn_host, sizeof(SlabDyn)));
         if (rc == 0) memset(s.dyn_host, 0, sizeof(SlabDyn));
         fail_cuda(cudaMalloc(&s.stats_dev, 2 * sizeof(double)));
+        fail_cuda(cudaMalloc(&s.info_dev, 24 * sizeof(int)));
         for (int k = 0; k < kMsgKinds && rc == 0; ++k) {
             for (int side = 0; side < 2 && rc == 0; ++side) {
                 rc = alloc_msg(&s.send[k][side], c->msg_bytes[k]);
@@ -524,6 +524,7 @@ void sph_cluster_destroy(sph_cluster *c) {
         if (s.ev_out_done) cudaEventDestroy(s.ev_out_done);
         cudaFree(s.dyn);
         cudaFree(s.stats_dev);
+        cudaFree(s.info_dev);
         cudaFree(s.out_stage);
         if (s.dyn_host) cudaFreeHost(s.dyn_host);
         if (s.host_records) cudaFreeHost(s.host_records);
@@ -772,71 +773,99 @@ int64_t sph_cluster_launch_count(sph_cluster *c) { return c ? c->launches : 0; }
 
 // ---- load rebalancing ---------------------------------------------------------------------------
 // Every boundary between two slabs moves by at most one layer towards the lighter slab, when that
-// reduces the difference of their particle counts.  The particles of a layer that changes owner
-// are sent through the ordinary migration messages: k_rekey_emigrate marks everything outside the
-// new range as emigrated and re-keys the rest for the new local layer numbering.
+// reduces the difference of their particle counts.  A decision needs the two slabs' numbers only,
+// so neighbours swap five integers (the same point-to-point channels as the halos; no collective)
+// and both sides reach the same verdict.  The particles of a layer that changes owner are sent
+// through the ordinary migration messages: k_rekey_emigrate marks everything outside the new range
+// as emigrated and re-keys the rest for the new local layer numbering.
+struct SlabInfo5 {
+    int n_live, lo_count, hi_count, layers, max_layers;
+};
+
+static int boundary_move(const SlabInfo5 &below, const SlabInfo5 &above) {
+    const long long a = below.n_live, b = above.n_live;
+    // -1: the slab below hands its top layer up; +1: the slab above hands its bottom layer down.
+    // A slab keeps >= 3 layers and stays inside its cell table even if both its faces move.
+    if (a - b > below.hi_count && below.hi_count > 0 && below.layers >= 5 && above.layers <= above.max_layers - 2) return -1;
+    if (b - a > above.lo_count && above.lo_count > 0 && above.layers >= 5 && below.layers <= below.max_layers - 2) return +1;
+    return 0;
+}
+
 int sph_cluster_rebalance(sph_cluster *c) {
     if (!c) return sph_internal_fail(SPH_E_INVALID, "null cluster");
     c->steps_since_rebalance = 0;
     const int W = c->opt.world;
     if (W == 1) return 0;
-    int rc = sync_all(c);
+    int rc = sync_all(c);   // the pinned SlabDyn mirrors are those of the last step now
     if (rc) return rc;
-    // per rank: live particles and the population of its lowest / highest owned layer
-    std::vector<int> info((size_t)3 * W, 0);
-    for (Slab &s : c->slabs) {
-        CU(cudaSetDevice(s.device));
-        const Params &p = *s.core.p;
-        const uint32_t nn = (uint32_t)p.nc * p.nc;
-        uint32_t b[4];
-        const size_t at[4] = {nn, 2 * (size_t)nn, (size_t)nn * (p.ncz - 2), (size_t)nn * (p.ncz - 1)};
-        for (int i = 0; i < 4; ++i) CU(cudaMemcpy(&b[i], s.core.d->cell_start + at[i], 4, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost));
-        info[3 * s.rank] = s.dyn_host->n_live;
-        info[3 * s.rank + 1] = s.dyn_host->steps ? (int)(b[1] - b[0]) : 0;
-        info[3 * s.rank + 2] = s.dyn_host->steps ? (int)(b[3] - b[2]) : 0;
+    const size_t L = c->slabs.size();
+    std::vector<SlabInfo5> mine(L), nb_lo(L), nb_hi(L);
+    for (size_t i = 0; i < L; ++i) {
+        Slab &s = c->slabs[i];
+        const SlabDyn &h = *s.dyn_host;
+        mine[i] = SlabInfo5{h.n_live, h.steps ? h.lo_count : 0, h.steps ? h.hi_count : 0, s.zhi - s.zlo,
+                            c->max_layers[s.rank]};
     }
-    if (c->opt.local_count < W) {   // one process per GPU: all-gather the triples
-        Slab &s = c->slabs[0];
+    // neighbours' numbers: local ones directly, remote ones over send / recv
+    for (size_t i = 0; i < L; ++i) {
+        Slab &s = c->slabs[i];
         CU(cudaSetDevice(s.device));
-        int *dev = nullptr;
-        CU(cudaMalloc(&dev, sizeof(int) * 3 * (size_t)W));
-        CU(cudaMemcpy(dev + 3 * s.rank, &info[3 * s.rank], sizeof(int) * 3, cudaMemcpyHostToDevice));
-        NC(g_nccl.AllGather(dev + 3 * s.rank, dev, 3, ncclInt32, s.comm, s.core.stream));
-        CU(cudaStreamSynchronize(s.core.stream));
-        CU(cudaMemcpy(info.data(), dev, sizeof(int) * 3 * (size_t)W, cudaMemcpyDeviceToHost));
-        cudaFree(dev);
-    }
-    // decisions, identical on every process
-    std::vector<int> zlo = c->zlo, zhi = c->zhi;
-    bool any = false;
-    for (int r = 0; r + 1 < W; ++r) {
-        const long long a = info[3 * r], b = info[3 * (r + 1)];
-        const long long top_a = info[3 * r + 2], bottom_b = info[3 * (r + 1) + 1];
-        // move a's top layer up to b if that shrinks |a - b|, or b's bottom layer down to a; a slab
-        // keeps at least 3 layers and stays within its cell table (both known on every process)
-        if (a - b > top_a && top_a > 0 && zhi[r] - zlo[r] > 3 && zhi[r + 1] - zlo[r + 1] < c->max_layers[r + 1]) {
-            zhi[r] -= 1; zlo[r + 1] -= 1; any = true;
-        } else if (b - a > bottom_b && bottom_b > 0 && zhi[r + 1] - zlo[r + 1] > 3 && zhi[r] - zlo[r] < c->max_layers[r]) {
-            zhi[r] += 1; zlo[r + 1] += 1; any = true;
+        bool grouped = false;
+        for (int side = 0; side < 2; ++side) {
+            const int peer = side ? s.rank + 1 : s.rank - 1;
+            if (peer < 0 || peer >= W) continue;
+            if (is_local(c, peer)) {
+                (side ? nb_hi : nb_lo)[i] = mine[peer - c->opt.first_rank];
+            } else {
+                if (!grouped) {
+                    CU(cudaMemcpyAsync(s.info_dev, &mine[i], sizeof(SlabInfo5), cudaMemcpyHostToDevice, s.core.stream));
+                    NC(g_nccl.GroupStart());
+                    grouped = true;
+                }
+                NC(g_nccl.Send(s.info_dev, sizeof(SlabInfo5), ncclChar, peer, s.comm, s.core.stream));
+                NC(g_nccl.Recv(s.info_dev + 8 * (1 + side), sizeof(SlabInfo5), ncclChar, peer, s.comm, s.core.stream));
+            }
+        }
+        if (grouped) {
+            NC(g_nccl.GroupEnd());
+            int host[24];
+            CU(cudaMemcpyAsync(host, s.info_dev, sizeof host, cudaMemcpyDeviceToHost, s.core.stream));
+            CU(cudaStreamSynchronize(s.core.stream));
+            if (s.rank > 0 && !is_local(c, s.rank - 1)) memcpy(&nb_lo[i], host + 8, sizeof(SlabInfo5));
+            if (s.rank + 1 < W && !is_local(c, s.rank + 1)) memcpy(&nb_hi[i], host + 16, sizeof(SlabInfo5));
         }
     }
-    if (!any) return 0;
-    for (Slab &s : c->slabs) {
+    bool any = false;
+    std::vector<int> new_lo(L), new_hi(L);
+    for (size_t i = 0; i < L; ++i) {
+        Slab &s = c->slabs[i];
+        new_lo[i] = s.zlo + (s.rank > 0 ? boundary_move(nb_lo[i], mine[i]) : 0);
+        new_hi[i] = s.zhi + (s.rank + 1 < W ? boundary_move(mine[i], nb_hi[i]) : 0);
+        any = any || new_lo[i] != s.zlo || new_hi[i] != s.zhi;
+    }
+    // Whether ANY boundary of the job moved is not known here (a process only sees its own faces),
+    // so the migration round below always runs when slabs are remote; it is skipped only when every
+    // slab is local and nothing moved.
+    if (!any && c->opt.local_count == W) return 0;
+    for (size_t i = 0; i < L; ++i) {
+        Slab &s = c->slabs[i];
         CU(cudaSetDevice(s.device));
-        if (zlo[s.rank] != s.zlo || zhi[s.rank] != s.zhi) {
-            apply_range(s, zlo[s.rank], zhi[s.rank]);
+        const bool moved = new_lo[i] != s.zlo || new_hi[i] != s.zhi;
+        if (moved) {
+            apply_range(s, new_lo[i], new_hi[i]);
+            c->zlo[s.rank] = new_lo[i];
+            c->zhi[s.rank] = new_hi[i];
             s.rebalances += 1;
         }
         rc = wait_taken(c, s, kMigrate);
         if (rc) return rc;
         for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(s.send[kMigrate][side], 0, sizeof(MsgHeader), s.core.stream));
-        Params p = launch_params(s, c->cap);
-        launch_rekey_emigrate(p, *s.core.d, s.core.stream);
-        c->launches += 1;
+        if (moved) {
+            const Params p = launch_params(s, c->cap);
+            launch_rekey_emigrate(p, *s.core.d, s.core.stream);
+            c->launches += 1;
+        }
     }
-    c->zlo = zlo;
-    c->zhi = zhi;
     rc = exchange(c, kMigrate);
     if (rc) return rc;
     for (Slab &s : c->slabs) {

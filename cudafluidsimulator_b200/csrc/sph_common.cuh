@@ -29,6 +29,7 @@ struct SlabDyn {
     int steps;          // steps taken (statistics)
     unsigned overflow;  // SPH_OVF_* bits: a capacity was exceeded, particles were lost
     int n_prev;         // live particles of the step that just finished (its rho / pa slots)
+    int lo_count, hi_count;        // particles in the lowest / highest owned layer (this step's sort)
     unsigned long long migrated;   // particles received from neighbours so far (statistics)
     unsigned long long ghosts;     // ghost particles installed so far (statistics)
 };

@@ -167,6 +167,13 @@ class Simulator:
         N.check(self._lib.sph_get_sorted_index(self._h, _ptr(ids, C.c_uint32), _ptr(keys, C.c_uint32)))
         return ids, keys
 
+    @property
+    def table_size(self) -> int:
+        """Number of distinct cell keys of the sort (flat: cells; Morton: 8^bits)."""
+        size = C.c_uint32()
+        N.check(self._lib.sph_get_cell_start(self._h, None, C.byref(size)))
+        return int(size.value)
+
     def get_cell_start(self) -> np.ndarray:
         size = C.c_uint32()
         N.check(self._lib.sph_get_cell_start(self._h, None, C.byref(size)))
