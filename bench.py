@@ -526,6 +526,20 @@ def run_ours(args, wl, rank, local_rank, world):
     stage_ms = {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]}
     sim.close()
 
+    # -- BASELINE configs[2] names "Morton-sorted cells": the same steps with Morton keys, same run
+    morton = None
+    if args.key == "flat" and not args.no_morton:
+        libc.srand(1)
+        sm = sph.Simulator(st, key_mode=sph.SPH_KEY_MORTON, device=local_rank)
+        sm.setup()
+        sm.advance(args.warmup)
+        mms = sm.advance_timed(args.steps)
+        sm.close()
+        morton = {"ms_per_step": mms / args.steps, "value": n * args.steps / (mms * 1e-3),
+                  "relative_to_flat": (mms / args.steps) / (ms / args.steps),
+                  "why": "Morton order breaks the 3 x-neighbours of a row into separate runs (27 single-cell runs "
+                         "per stencil instead of 9 contiguous x-runs), see profiles/r02_morton_vs_flat.md"}
+
     # -- e2e: same workload through sph_step() with the per-step D2H of positions --------
     def e2e_run(pipeline):
         libc.srand(1)
@@ -632,6 +646,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": roof,
         "stages": stages,
+        "key_morton": morton,
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
@@ -699,6 +714,7 @@ def main():
                          "(BASELINE configs[4], the north_star weak-scaling point)")
     ap.add_argument("--key", default="flat", choices=["flat", "morton"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-morton", action="store_true", help="skip the Morton-key run of the same steps")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = the N=1 workload per GPU (default); strong = --total particles split over the GPUs")
     ap.add_argument("--total", type=int, default=64_000_000, help="global particle count for --scaling strong")

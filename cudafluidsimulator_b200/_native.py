@@ -51,20 +51,6 @@ class SphOptions(C.Structure):
     ]
 
 
-class SphSlabInfo(C.Structure):
-    _fields_ = [("n_owned", C.c_int32), ("n_total", C.c_int32), ("slot0", C.c_int32),
-                ("lo_first", C.c_int32), ("lo_count", C.c_int32),
-                ("hi_first", C.c_int32), ("hi_count", C.c_int32),
-                ("emig_count", C.c_int32 * 2), ("overflow", C.c_int32)]
-
-
-class SphSlabBuffers(C.Structure):
-    _fields_ = [("srt_pos", C.c_void_p), ("srt_vel", C.c_void_p), ("pa", C.c_void_p),
-                ("cur_pos", C.c_void_p), ("cur_vel", C.c_void_p),
-                ("emig_pos", C.c_void_p * 2), ("emig_vel", C.c_void_p * 2), ("counts", C.c_void_p),
-                ("capacity", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32)]
-
-
 SPH_NCCL_ID_BYTES = 128
 SPH_MAX_LOCAL_SLABS = 16
 
@@ -81,7 +67,8 @@ class SphSlabStats(C.Structure):
     _fields_ = [("rank", C.c_int32), ("device", C.c_int32), ("z_cell_lo", C.c_int32), ("z_cell_hi", C.c_int32),
                 ("n_owned", C.c_int32), ("ghosts_lo", C.c_int32), ("ghosts_hi", C.c_int32), ("steps", C.c_int32),
                 ("migrated_total", C.c_int64), ("ghosts_total", C.c_int64), ("overflow", C.c_uint32),
-                ("rebalances", C.c_int32), ("kinetic_energy", C.c_double), ("density_sum", C.c_double)]
+                ("rebalances", C.c_int32), ("kinetic_energy", C.c_double), ("density_sum", C.c_double),
+                ("debug_flags", C.c_uint32), ("checked_build", C.c_int32)]
 
 
 # every symbol include/sph_b200.h declares: name -> (restype, argtypes)
@@ -111,20 +98,6 @@ SYMBOLS = {
     "sph_get_density_pressure_force": (C.c_int, [_P, _F, _F, _F]),
     "sph_get_stats": (C.c_int, [_P, _D, _D]),
     "sph_slab_load": (C.c_int, [_P, C.c_int, _F, _F, _U]),
-    "sph_slab_build": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
-    "sph_slab_build_async": (C.c_int, [_P]),
-    "sph_slab_build_finish": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
-    "sph_slab_force_async": (C.c_int, [_P]),
-    "sph_slab_force_finish": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
-    "sph_slab_density": (C.c_int, [_P, C.c_int, C.c_int]),
-    "sph_slab_interior_ctas": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "sph_slab_density_part": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "sph_slab_force_part": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
-    "sph_slab_force": (C.c_int, [_P, C.POINTER(SphSlabInfo)]),
-    "sph_slab_append": (C.c_int, [_P, C.c_int]),
-    "sph_slab_buffers": (C.c_int, [_P, C.POINTER(SphSlabBuffers)]),
-    "sph_slab_download": (C.c_int, [_P, _U, _F, _F, _I]),
-    "sph_set_stream": (C.c_int, [_P, C.c_void_p]),
     "sph_cluster_nccl_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "sph_cluster_create": (C.c_int, [C.POINTER(SphSettings), C.POINTER(SphClusterOptions), C.POINTER(_P)]),
     "sph_cluster_destroy": (None, [_P]),

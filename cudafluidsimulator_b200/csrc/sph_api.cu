@@ -72,13 +72,6 @@ struct sph_sim {
     // slab mode
     int ghost_cap = 0;          // == p.slot0
     uint32_t table_capacity = 0;   // cell_start entries allocated (slab: room for the layer range to grow)
-    int n_total = 0;            // entries of the cur arrays in use
-    int n_dead = 0;             // of which emigrated (dropped by the next build)
-    int hashed_upto = 0;        // keys of cur[0, hashed_upto) are valid
-    int slab_overflow = 0;
-    uint32_t *slab_counts = nullptr;       // device: [0..3] boundary-layer slot bounds, [4..5] emigrant counts
-    uint32_t *slab_counts_host = nullptr;  // pinned mirror, filled asynchronously
-    int pending_n_sort = 0, pending_n_live = 0;
     bool keys_valid = false;    // d.key matches d.cur_pos
     bool step_valid = false;    // srt_*/cell_start/rho/pa describe the last step
     cudaGraphExec_t graph = nullptr;       // step graph writing out_buf[0]
@@ -91,7 +84,6 @@ struct sph_sim {
     bool spec_inflight = false;            // a step is enqueued whose positions were not handed out yet
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
-    cudaEvent_t ev_build = nullptr;   // slab mode: the counts of sph_slab_build_async() reached the host
     bool profiling = false;
     std::vector<EventPair> events;
     size_t events_used = 0;
@@ -292,15 +284,10 @@ int free_device(sph_sim *s) {
     s->out_buf[0] = s->out_buf[1] = nullptr;
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_step) cudaEventDestroy(s->ev_step);
-    if (s->ev_build) cudaEventDestroy(s->ev_build);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     s->copy_stream = nullptr;
-    s->ev_step = s->ev_build = s->ev_copy = nullptr;
-    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.nbits); cudaFree(d.pair_xy); cudaFree(d.pair_z);
-    for (int sd = 0; sd < 2; ++sd) { cudaFree(d.emig_pos[sd]); cudaFree(d.emig_vel[sd]); }
-    cudaFree(s->slab_counts);   // d.emig_count points into it
-    if (s->slab_counts_host) cudaFreeHost(s->slab_counts_host);
-    s->slab_counts = s->slab_counts_host = nullptr;
+    s->ev_step = s->ev_copy = nullptr;
+    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.masks.words); cudaFree(d.masks.base); cudaFree(d.masks.cursor); cudaFree(d.pair_xy); cudaFree(d.pair_z);
     cudaFree(s->p.dbg);
     s->p.dbg = nullptr;
     memset(&d, 0, sizeof(d));
@@ -481,16 +468,8 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
         s->ghost_cap = g;
         s->p.slot0 = g;
         scap = cap + 2 * (size_t)g;
-        d.emig_capacity = s->opt.emig_capacity > 0 ? s->opt.emig_capacity : (int)(cap / 16) + 1024;
-        for (int sd = 0; sd < 2; ++sd) {
-            CU(cudaMalloc(&d.emig_pos[sd], (size_t)d.emig_capacity * sizeof(float4)));
-            CU(cudaMalloc(&d.emig_vel[sd], (size_t)d.emig_capacity * sizeof(float4)));
-        }
-        CU(cudaMalloc(&s->slab_counts, 8 * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(s->slab_counts, 0, 8 * sizeof(uint32_t), s->stream));
-        CU(cudaMallocHost(&s->slab_counts_host, 8 * sizeof(uint32_t)));
-        d.emig_count[0] = s->slab_counts + 4;
-        d.emig_count[1] = s->slab_counts + 5;
+        // (emigrants go straight into the cluster's migration messages: sph_cluster.cu points
+        // d.emig_* at them)
     }
     CU(cudaMalloc(&d.cur_pos, cap * sizeof(float4)));
     CU(cudaMalloc(&d.cur_vel, cap * sizeof(float4)));
@@ -528,9 +507,15 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
         d.stage_tiles = s->opt.stage_tiles ? 1 : 0;
         d.density_exact = s->opt.density_sum == 2 ? 0 : (s->opt.density_sum == 1 ? 1 : kDefaultDensityExact);
     }
-    if (s->p.key_mode == SPH_KEY_FLAT && !s->opt.no_mask_handoff) {
-        const size_t ctas = (cap + kBlock - 1) / kBlock;
-        CU(cudaMalloc(&d.nbits, ctas * kMaskWords * kBlock * sizeof(uint32_t)));
+    if (s->p.key_mode == SPH_KEY_FLAT) {
+        const size_t warps = (cap + kBlock - 1) / kBlock * (kBlock / 32);
+        CU(cudaMalloc(&d.masks.base, warps * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(d.masks.base, 0xff, warps * sizeof(uint32_t), s->stream));
+        CU(cudaMalloc(&d.masks.cursor, kMaskPools * 32 * sizeof(uint32_t)));
+        if (!s->opt.no_mask_handoff) {
+            d.masks.rows = (uint32_t)((warps * kMaskRowsPerWarp + kMaskPools - 1) / kMaskPools + 64);
+            CU(cudaMalloc(&d.masks.words, (size_t)d.masks.rows * kMaskPools * 32 * sizeof(uint32_t)));
+        }
     }
     CU(cudaMemsetAsync(d.cell_start, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t), s->stream));
     CU(cudaMemsetAsync(d.rho, 0, scap * sizeof(float), s->stream));
@@ -946,28 +931,6 @@ int sph_get_stats(sph_sim *s, double *ke, double *mean_rho) {
         if (!(s)->p.slab) return fail(SPH_E_STATE, "simulator was not created in slab mode"); \
     } while (0)
 
-int sph_set_stream(sph_sim *s, void *cuda_stream) {
-    REQUIRE_SETUP(s);
-    CU(cudaStreamSynchronize(s->stream));
-    drop_graph(s);
-    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
-    s->stream = (cudaStream_t)cuda_stream;
-    s->own_stream = false;
-    return 0;
-}
-
-int sph_slab_buffers(sph_sim *s, SphSlabBuffers *out) {
-    REQUIRE_SLAB(s);
-    if (!out) return fail(SPH_E_INVALID, "null argument");
-    const DeviceState &d = s->d;
-    out->srt_pos = d.srt_pos; out->srt_vel = d.srt_vel; out->pa = d.pa;
-    out->cur_pos = d.cur_pos; out->cur_vel = d.cur_vel;
-    for (int sd = 0; sd < 2; ++sd) { out->emig_pos[sd] = d.emig_pos[sd]; out->emig_vel[sd] = d.emig_vel[sd]; }
-    out->counts = s->slab_counts;
-    out->capacity = s->capacity; out->ghost_capacity = s->ghost_cap; out->emig_capacity = d.emig_capacity;
-    return 0;
-}
-
 int sph_slab_load(sph_sim *s, int n, const float *pos, const float *vel, const uint32_t *ids) {
     REQUIRE_SLAB(s);
     if (n < 0 || n > s->capacity) return fail(SPH_E_INVALID, "n = %d exceeds the capacity %d", n, s->capacity);
@@ -984,248 +947,7 @@ int sph_slab_load(sph_sim *s, int n, const float *pos, const float *vel, const u
         CU(cudaMemcpyAsync(s->d.cur_vel, hv.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
-    s->n_total = n; s->n_dead = 0; s->hashed_upto = 0; s->p.n = n; s->step_valid = false;
-    return 0;
-}
-
-int sph_slab_append(sph_sim *s, int count) {
-    REQUIRE_SLAB(s);
-    if (count < 0 || s->n_total + count > s->capacity) {
-        s->slab_overflow |= 1;
-        return fail(SPH_E_INVALID, "appending %d particles to %d exceeds the capacity %d", count, s->n_total, s->capacity);
-    }
-    s->n_total += count;
-    return 0;
-}
-
-// Enqueue only: hash of new arrivals, sort, reorder; the four slot bounds of the two boundary
-// layers land in slab_counts[0..3] (device, for sending to the neighbours without a host round
-// trip) and, asynchronously, in the pinned mirror read by sph_slab_build_finish().
-int sph_slab_build_async(sph_sim *s) {
-    REQUIRE_SLAB(s);
-    Params &p = s->p;
-    const int n_sort = s->n_total;
-    const int n_live = s->n_total - s->n_dead;
-    const uint32_t nn = (uint32_t)p.nc * p.nc;
-    if (n_sort > 0) {
-        // keys of freshly arrived particles (everything after a load)
-        if (s->hashed_upto < n_sort) {
-            stage_begin(s, kStHash);
-            launch_hash_range(p, s->d, s->hashed_upto, n_sort - s->hashed_upto, s->stream);
-            stage_end(s);
-        }
-        SortHooks hooks{s, sort_before, sort_after};
-        s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], n_sort, s->passes,
-                                         s->d.sort_scratch, s->sm_count, s->stream, &hooks);
-    }
-    p.n = n_live;   // emigrated particles carry dead_key and sit behind the live ones
-    s->d.sorted_pairs = s->d.pairs[s->sorted_buf];
-    stage_begin(s, kStReorder);
-    launch_reorder(p, s->d, s->sorted_buf, n_sort, s->sm_count, s->stream);
-    stage_end(s);
-    // slot bounds of the lowest (local layer 1) and highest (local layer ncz-2) owned layers
-    const uint32_t *cs = s->d.cell_start;
-    const size_t at[4] = {nn, 2 * (size_t)nn, (size_t)nn * (p.ncz - 2), (size_t)nn * (p.ncz - 1)};
-    for (int i = 0; i < 4; ++i)
-        CU(cudaMemcpyAsync(s->slab_counts + i, cs + at[i], 4, cudaMemcpyDeviceToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->slab_counts_host, s->slab_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    if (!s->ev_build) CU(cudaEventCreateWithFlags(&s->ev_build, cudaEventDisableTiming));
-    CU(cudaEventRecord(s->ev_build, s->stream));
-    s->pending_n_sort = n_sort;
-    s->pending_n_live = n_live;
-    return 0;
-}
-
-int sph_slab_build_finish(sph_sim *s, SphSlabInfo *info) {
-    REQUIRE_SLAB(s);
-    if (!info) return fail(SPH_E_INVALID, "null argument");
-    memset(info, 0, sizeof(*info));
-    // waits for the build only: work the caller enqueued behind it (a speculative interior density
-    // launch, sph_slab_density_part) keeps the GPU busy across this host round trip
-    if (s->profiling || !s->ev_build) {
-        int rc = sync_stream(s);
-        if (rc) return rc;
-    } else {
-        CU(cudaEventSynchronize(s->ev_build));
-    }
-    const uint32_t *b = s->slab_counts_host;
-    const int n_live = s->pending_n_live;
-    s->n_total = n_live; s->n_dead = 0; s->hashed_upto = n_live;
-    info->n_owned = n_live; info->n_total = n_live; info->slot0 = s->p.slot0;
-    info->lo_first = (int)b[0]; info->lo_count = (int)(b[1] - b[0]);
-    info->hi_first = (int)b[2]; info->hi_count = (int)(b[3] - b[2]);
-    if (info->lo_count > s->ghost_cap || info->hi_count > s->ghost_cap) s->slab_overflow |= 2;
-    info->overflow = s->slab_overflow;
-    return 0;
-}
-
-int sph_slab_build(sph_sim *s, SphSlabInfo *info) {
-    int rc = sph_slab_build_async(s);
-    return rc ? rc : sph_slab_build_finish(s, info);
-}
-
-int sph_slab_density(sph_sim *s, int g_lo, int g_hi) {
-    REQUIRE_SLAB(s);
-    if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
-        return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
-    s->p.slot_begin = s->p.slot0 - g_lo;
-    s->p.slot_end = s->p.slot0 + s->p.n + g_hi;
-    const Params &p = s->p;
-    const uint32_t nn = (uint32_t)p.nc * p.nc;
-    stage_begin(s, kStReorder);
-    launch_ghost_prepare(p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
-    stage_end(s);
-    stage_begin(s, kStReorder);
-    launch_ghost_prepare(p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
-    stage_end(s);
-    if (p.n > 0) {
-        stage_begin(s, kStDensity);
-        launch_density(p, s->th, s->d, false, s->stream);
-        stage_end(s);
-    }
-    s->step_valid = true;
-    return 0;
-}
-
-// Enqueue only: force + integrate; emigrant counts land in slab_counts[4..5] (device) and in
-// the pinned mirror.
-int sph_slab_force_async(sph_sim *s) {
-    REQUIRE_SLAB(s);
-    CU(cudaMemsetAsync(s->slab_counts + 4, 0, 2 * sizeof(uint32_t), s->stream));
-    if (s->p.n > 0) {
-        stage_begin(s, kStForce);
-        launch_force_integrate(s->p, s->th, s->d, s->stream);
-        stage_end(s);
-    }
-    CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->slab_counts + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    return 0;
-}
-
-// ---- interior / boundary split: lets the caller run the halo exchanges under the interior CTAs ----
-// Particle CTAs [a, b) hold no particle of the lowest / highest owned layer: they need no ghost
-// data (density: positions, force: {p, a}).  Valid after sph_slab_build_finish().
-static void interior_ctas(const sph_sim *s, int *a, int *b) {
-    const uint32_t *c = s->slab_counts_host;   // lo_first, lo_end, hi_first, hi_end (sorted slots)
-    const int lo_end = (int)c[1] - s->p.slot0, hi_first = (int)c[2] - s->p.slot0;
-    *a = std::min((std::max(lo_end, 0) + kBlock - 1) / kBlock, (s->p.n + kBlock - 1) / kBlock);
-    *b = std::max(std::min(hi_first, s->p.n), 0) / kBlock;
-    if (*b < *a) *b = *a;
-}
-
-int sph_slab_interior_ctas(sph_sim *s, int *cta_a, int *cta_b) {
-    REQUIRE_SLAB(s);
-    if (!cta_a || !cta_b) return fail(SPH_E_INVALID, "null argument");
-    interior_ctas(s, cta_a, cta_b);
-    return 0;
-}
-
-static int part_params(sph_sim *s, int part, int a, int b, Params *out) {
-    Params p = s->p;
-    const int total = (p.n + kBlock - 1) / kBlock;
-    if ((part != 0 && part != 1) || a < 0 || b < a)
-        return fail(SPH_E_INVALID, "part %d of particle CTAs [%d, %d) is not valid", part, a, b);
-    // a range guessed before the particle count was known may reach past the end: both parts clamp
-    // it the same way (the caller compares its guess with sph_slab_interior_ctas() anyway)
-    a = std::min(a, total);
-    b = std::min(b, total);
-    if (part == 0) { p.cta_gap_at = 0; p.cta_gap_len = a; p.cta_count = b - a; }
-    else { p.cta_gap_at = a; p.cta_gap_len = b - a; p.cta_count = total - (b - a); }
-    *out = p;
-    return 0;
-}
-
-int sph_slab_density_part(sph_sim *s, int part, int cta_a, int cta_b, int g_lo, int g_hi) {
-    REQUIRE_SLAB(s);
-    Params p;
-    int rc = part_params(s, part, cta_a, cta_b, &p);
-    if (rc) return rc;
-    if (part == 0) {
-        p.slot_begin = p.slot0;
-        p.slot_end = p.slot0 + p.n;
-    } else {
-        if (g_lo < 0 || g_hi < 0 || g_lo > s->ghost_cap || g_hi > s->ghost_cap)
-            return fail(SPH_E_INVALID, "ghost counts (%d, %d) exceed the ghost capacity %d", g_lo, g_hi, s->ghost_cap);
-        s->p.slot_begin = p.slot_begin = p.slot0 - g_lo;
-        s->p.slot_end = p.slot_end = p.slot0 + p.n + g_hi;
-        const uint32_t nn = (uint32_t)p.nc * p.nc;
-        stage_begin(s, kStReorder);
-        launch_ghost_prepare(s->p, s->d, p.slot0 - g_lo, g_lo, 0u, nn, s->stream);
-        stage_end(s);
-        stage_begin(s, kStReorder);
-        launch_ghost_prepare(s->p, s->d, p.slot0 + p.n, g_hi, nn * (uint32_t)(p.ncz - 1), nn * (uint32_t)p.ncz, s->stream);
-        stage_end(s);
-        s->step_valid = true;
-    }
-    if (p.cta_count > 0) {
-        stage_begin(s, kStDensity);
-        launch_density(p, s->th, s->d, false, s->stream);
-        stage_end(s);
-    }
-    return 0;
-}
-
-int sph_slab_force_part(sph_sim *s, int part, int cta_a, int cta_b) {
-    REQUIRE_SLAB(s);
-    Params p;
-    int rc = part_params(s, part, cta_a, cta_b, &p);
-    if (rc) return rc;
-    if (part == 0) CU(cudaMemsetAsync(s->slab_counts + 4, 0, 2 * sizeof(uint32_t), s->stream));
-    if (p.cta_count > 0) {
-        stage_begin(s, kStForce);
-        launch_force_integrate(p, s->th, s->d, s->stream);
-        stage_end(s);
-    }
-    if (part == 1)
-        CU(cudaMemcpyAsync(s->slab_counts_host + 4, s->slab_counts + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    return 0;
-}
-
-int sph_slab_force_finish(sph_sim *s, SphSlabInfo *info) {
-    REQUIRE_SLAB(s);
-    if (!info) return fail(SPH_E_INVALID, "null argument");
-    memset(info, 0, sizeof(*info));
-    int rc = sync_stream(s);
-    if (rc) return rc;
-    const uint32_t *cnt = s->slab_counts_host + 4;
-    for (int sd = 0; sd < 2; ++sd) {
-        if ((int)cnt[sd] > s->d.emig_capacity) s->slab_overflow |= 4;
-        info->emig_count[sd] = (int)std::min<uint32_t>(cnt[sd], (uint32_t)s->d.emig_capacity);
-    }
-    s->n_dead = (int)(cnt[0] + cnt[1]);
-    info->n_owned = s->p.n - s->n_dead; info->n_total = s->n_total; info->slot0 = s->p.slot0;
-    info->overflow = s->slab_overflow;
-    return 0;
-}
-
-int sph_slab_force(sph_sim *s, SphSlabInfo *info) {
-    int rc = sph_slab_force_async(s);
-    return rc ? rc : sph_slab_force_finish(s, info);
-}
-
-int sph_slab_download(sph_sim *s, uint32_t *ids, float *pos, float *vel, int *n_out) {
-    REQUIRE_SLAB(s);
-    const int n = s->n_total;
-    std::vector<float4> hp((size_t)n), hv((size_t)n);
-    std::vector<uint32_t> hk((size_t)n);
-    if (n) {
-        if (s->hashed_upto < n) {   // keys are needed to tell dead entries apart
-            launch_hash_range(s->p, s->d, s->hashed_upto, n - s->hashed_upto, s->stream);
-            s->hashed_upto = n;
-        }
-        CU(cudaMemcpyAsync(hp.data(), s->d.cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(hv.data(), s->d.cur_vel, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(hk.data(), s->d.key, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
-    }
-    CU(cudaStreamSynchronize(s->stream));
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
-        if (s->n_dead > 0 && hk[i] == s->p.dead_key) continue;
-        if (ids) ids[m] = id_of(hp[i]);
-        if (pos) { pos[3 * m] = hp[i].x; pos[3 * m + 1] = hp[i].y; pos[3 * m + 2] = hp[i].z; }
-        if (vel) { vel[3 * m] = hv[i].x; vel[3 * m + 1] = hv[i].y; vel[3 * m + 2] = hv[i].z; }
-        ++m;
-    }
-    if (n_out) *n_out = m;
+    s->p.n = n; s->step_valid = false;
     return 0;
 }
 

@@ -427,7 +427,6 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
         so.z_cell_hi = c->zhi[s.rank];
         so.nz_cells = nz;
         so.ghost_capacity = c->cap_g;
-        so.emig_capacity = 1;   // the migration messages below replace the classic emigrant buffers
         so.density_sum = o->density_sum;
         rc = sph_create_ex(&ss, &so, &s.sim);
         if (rc == 0) rc = sph_setup(s.sim);
@@ -457,8 +456,6 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
         // the force kernel appends emigrants straight into the migration messages
         DeviceState &d = *s.core.d;
         for (int side = 0; side < 2; ++side) {
-            cudaFree(d.emig_pos[side]);
-            cudaFree(d.emig_vel[side]);
             d.emig_pos[side] = reinterpret_cast<float4 *>(s.send[kMigrate][side] + 1);
             d.emig_vel[side] = d.emig_pos[side] + c->cap_m;
             d.emig_count[side] = &s.send[kMigrate][side]->count;
@@ -766,7 +763,7 @@ int sph_cluster_stats(sph_cluster *c, int li, SphSlabStats *out) {
     CU(cudaStreamSynchronize(s.core.stream));
     out->kinetic_energy = hs[0];
     out->density_sum = hs[1];
-    return 0;
+    return sph_debug_flags(s.sim, &out->debug_flags, &out->checked_build);
 }
 
 int64_t sph_cluster_launch_count(sph_cluster *c) { return c ? c->launches : 0; }

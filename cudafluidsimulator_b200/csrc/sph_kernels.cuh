@@ -27,8 +27,19 @@ struct DeviceState {
     int stage_tiles;             // 1: dense CTAs run k_density_tile (TMA-staged neighbour tiles)
     int density_exact;           // 1: density summed term by term in the reference's order (bit-identical
                                  // to the CPU restatement); 0: factored sum (DensityAcc in sph_kernels.cu)
-    uint32_t *nbits;             // in-range bit masks density hands to force; kMaskWords words
-                                 // per particle, [CTA][word][lane] interleaved
+    // In-range bit masks density hands to force.  A pool of rows of 32 words; every WARP of a
+    // particle CTA takes as many rows as its widest particle needs (word w of lane t = row base + w,
+    // column t) from a per-step bump allocator -- 2-3 rows in the undisturbed fluid, tens in the
+    // floor pile-up -- instead of a fixed kMaskWords rows per particle (4 GB at 16 M particles).
+    // The pool is split into kMaskPools segments with their own cursors (warp w uses segment
+    // w % kMaskPools) so that the allocating atomics do not serialise on one address.
+    struct MaskPool {
+        uint32_t *words;     // rows * 32 words
+        uint32_t *base;      // per warp of the particle CTAs: first row, or kNoMaskRows (segment
+                             // exhausted: the force kernel repeats the distance tests for that warp)
+        uint32_t *cursor;    // kMaskPools cursors, 128 bytes apart: rows handed out this step
+        uint32_t rows;       // capacity of ONE segment
+    } masks;
     // slab mode: particles that left the owned z-layers during integration, per side
     float4 *emig_pos[2], *emig_vel[2];   // [0] towards lower z, [1] towards higher z
     uint32_t *emig_count[2];             // one counter per side (may exceed emig_capacity: overflow)
@@ -43,6 +54,12 @@ struct MsgHeader {
 
 constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
 constexpr int kMaskWords = 64;   // mask capacity per particle: 64 words = up to 2048 candidates
+constexpr uint32_t kNoMaskRows = 0xffffffffu;
+constexpr int kMaskRowsPerWarp = 12;  // pool size: average rows per warp (48 B per particle)
+#ifndef SPH_MASK_POOLS
+#define SPH_MASK_POOLS 64
+#endif
+constexpr int kMaskPools = SPH_MASK_POOLS;
 
 // Predicate thresholds on r^2 that are exactly equivalent to the reference's
 // predicates on r = sqrt_rn(r^2) (ref: simulator.cu:110 `dist < EPS_F`,

@@ -88,7 +88,7 @@ typedef struct SphOptions {
     int32_t nz_cells;     /* slab mode: global cell layers along z (0 = numCellsPerDim); the
                              global box is boxDim x boxDim x nz_cells*h                  */
     int32_t ghost_capacity; /* slab mode: max ghost particles per side (0 = capacity/4)     */
-    int32_t emig_capacity;  /* slab mode: max emigrants per side and step (0 = capacity/16) */
+    int32_t emig_capacity;  /* unused (the cluster's migration messages hold the emigrants) */
     int32_t pipeline_readback; /* 1: sph_step() overlaps the device->host copy of step k with the
                              computation of step k+1 (started speculatively before sph_step
                              returns).  Positions handed out are exactly those of the blocking
@@ -159,82 +159,13 @@ int sph_get_density_pressure_force(sph_sim *sim, float *rho, float *prs, float *
 /* kinetic energy 0.5*m*|v|^2 summed, and mean density of the last step */
 int sph_get_stats(sph_sim *sim, double *kinetic_energy, double *mean_density);
 
-/* --- slab decomposition (multi-GPU; north_star: spatial slabs, per-step ghost halo
- * exchange and particle migration) ---------------------------------------------------
- * One simulator per GPU owns the global cell layers [z_cell_lo, z_cell_hi) along z
- * (SphOptions) and the particles in them.  The library does the compute and exposes the
- * device buffers; the caller moves halo / migrant ranges between ranks (NCCL send/recv
- * or P2P copies straight between these buffers, see cudafluidsimulator_b200/slab.py):
- *
- *   sph_slab_build    hash (new arrivals) + sort + reorder -> sorted owned particles at
- *                     slots [slot0, slot0+n_owned) of srt_pos/srt_vel; reports the slot
- *                     ranges of the lowest / highest owned layer (= what the neighbours
- *                     need as ghosts)
- *   [exchange A]      neighbours' boundary layers -> srt_pos/srt_vel ghost slots:
- *                     low ghosts end at slot0, high ghosts start at slot0+n_owned
- *   sph_slab_density  cell ranges of the ghosts, density + pressure of owned particles
- *   [exchange B]      pa of the boundary layers -> pa at the same ghost slots
- *   sph_slab_force    force + integrate owned particles; particles leaving the slab are
- *                     packed into emig_pos/emig_vel[side] and dropped at the next build
- *   [migration]       emigrants -> neighbour's cur_pos/cur_vel at index n_total onwards,
- *                     then sph_slab_append(count)
- * There is no reference equivalent (the reference is single-GPU). */
-typedef struct SphSlabInfo {
-    int32_t n_owned;      /* live owned particles                                   */
-    int32_t n_total;      /* entries of cur_pos/cur_vel in use (owned + appended)   */
-    int32_t slot0;        /* first owned sorted slot (= ghost capacity)             */
-    int32_t lo_first, lo_count; /* sorted slots of the lowest owned layer          */
-    int32_t hi_first, hi_count; /* sorted slots of the highest owned layer         */
-    int32_t emig_count[2];      /* emigrants of the last sph_slab_force (down, up) */
-    int32_t overflow;     /* non-zero: a capacity was exceeded, particles were lost */
-} SphSlabInfo;
-
-typedef struct SphSlabBuffers {   /* device pointers, valid until sph_destroy */
-    void *srt_pos, *srt_vel;      /* float4 per sorted slot                  */
-    void *pa;                     /* float2 per sorted slot                  */
-    void *cur_pos, *cur_vel;      /* float4 per particle, storage order      */
-    void *emig_pos[2], *emig_vel[2]; /* float4 per emigrant, per side        */
-    void *counts;                 /* uint32[8]: [0..3] slot bounds of the lowest / highest owned
-                                     layer (lo_first, lo_end, hi_first, hi_end), [4..5] emigrants
-                                     down / up -- device copies, to be sent to the neighbours
-                                     without a host round trip */
-    int32_t capacity, ghost_capacity, emig_capacity;
-} SphSlabBuffers;
-
+/* --- slab mode (building block of the multi-GPU cluster below) ------------------------------
+ * A simulator created with SphOptions.z_cell_lo < z_cell_hi owns the global cell layers
+ * [z_cell_lo, z_cell_hi) along z and the particles in them; its keys are local to the slab (layer 0
+ * and the last layer hold the neighbours' ghost particles).  Such a simulator is stepped by the
+ * cluster driver (sph_cluster_*), not by sph_step(); this call hands it its particle set. */
 /* Replace the owned particle set (host arrays; ids are global particle ids). */
 int sph_slab_load(sph_sim *sim, int n, const float *pos, const float *vel, const uint32_t *ids);
-int sph_slab_build(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
-/* Split forms: _async only enqueues (the counts also land in SphSlabBuffers.counts on the
- * device), _finish synchronises once and reports them -- lets the caller overlap the count
- * exchange with its neighbours with that one synchronisation. */
-int sph_slab_build_async(sph_sim *sim);
-int sph_slab_build_finish(sph_sim *sim, SphSlabInfo *info);
-int sph_slab_force_async(sph_sim *sim);
-int sph_slab_force_finish(sph_sim *sim, SphSlabInfo *info);
-int sph_slab_density(sph_sim *sim, int ghost_lo_count, int ghost_hi_count);
-int sph_slab_force(sph_sim *sim, SphSlabInfo *info);       /* = _async + _finish */
-/* The same two stages in two parts each, so that exchanges and host round trips run under
- * compute.  The particle CTAs (128 consecutive sorted particles) [cta_a, cta_b) are the
- * "interior": they must hold no particle of the lowest / highest owned layer, so they read no
- * ghost data.  sph_slab_interior_ctas() reports the largest such range (valid after
- * sph_slab_build_finish()); a caller may also enqueue part 0 with a narrower range guessed from
- * the previous step right behind sph_slab_build_async() -- sph_slab_build_finish() waits for the
- * build only -- and check the guess against sph_slab_interior_ctas() afterwards.
- *   part 0 = interior CTAs; part 1 = all the others, after the exchange completed (density:
- *   also builds the ghosts' cell ranges; force: also publishes the emigrant counts, i.e. it is
- *   followed by sph_slab_force_finish()).  Both parts of a stage take the same range.
- * Order per step: density 0, [A done], density 1, force 0, [B done], force 1.  Results are
- * identical to sph_slab_density() / sph_slab_force_async(). */
-int sph_slab_interior_ctas(sph_sim *sim, int *cta_a, int *cta_b);
-int sph_slab_density_part(sph_sim *sim, int part, int cta_a, int cta_b, int ghost_lo_count, int ghost_hi_count);
-int sph_slab_force_part(sph_sim *sim, int part, int cta_a, int cta_b);
-int sph_slab_append(sph_sim *sim, int count);
-int sph_slab_buffers(sph_sim *sim, SphSlabBuffers *out);
-/* Owned live particles (after sph_slab_force: the integrated state), any order. */
-int sph_slab_download(sph_sim *sim, uint32_t *ids, float *pos, float *vel, int *n);
-/* Run every launch of this simulator on the caller's CUDA stream (e.g. torch's current
- * stream, so that NCCL transfers and kernels are ordered without extra events). */
-int sph_set_stream(sph_sim *sim, void *cuda_stream);
 
 /* --- multi-GPU: a cluster of z-slabs, one per GPU -------------------------------------------
  * north_star: "the domain is partitioned across the 8xB200 box by a spatial slab decomposition,
@@ -284,6 +215,8 @@ typedef struct SphSlabStats {
     int32_t rebalances;             /* boundary moves applied so far                              */
     double kinetic_energy;          /* 0.5 m |v|^2 summed over the owned particles                */
     double density_sum;             /* sum of the last step's densities over its live particles   */
+    uint32_t debug_flags;           /* violation bits of the self-checking build (sph_debug_flags) */
+    int32_t checked_build;          /* 1 in the self-checking build                               */
 } SphSlabStats;
 
 /* A fresh NCCL unique id (rank 0 calls this and broadcasts the bytes by any means). */

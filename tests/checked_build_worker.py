@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import cudafluidsimulator_b200 as sph  # noqa: E402
-from cudafluidsimulator_b200.slab import LocalSlabCluster, SlabBackend, partition, slab_ranges  # noqa: E402
+from cudafluidsimulator_b200.cluster import Cluster, partition, slab_ranges  # noqa: E402
 from conftest import compressed_state, lattice_state, random_state  # noqa: E402
 
 total = 0
@@ -54,20 +54,18 @@ rng = np.random.default_rng(5)
 n = 20000
 pos = (np.float32([3.0, 3.0, 2.5]) + rng.uniform(0, 1.0, (n, 3)) * np.float32([1.5, 1.5, 5.0])).astype(np.float32)
 vel = (rng.standard_normal((n, 3)) * np.float32([0.5, 0.5, 6.0])).astype(np.float32)
-ranges = slab_ranges(100, 3)
-backends = []
-for (zlo, zhi), idx in zip(ranges, partition(pos, 0.1, ranges)):
-    b = SlabBackend(sph.Settings(numParticles=n), zlo, zhi, 100, capacity=n + 1024, ghost_capacity=n + 2, emig_capacity=n)
-    b.load(pos[idx], vel[idx], idx.astype(np.uint32))
-    backends.append(b)
-cl = LocalSlabCluster(backends)
-for _ in range(10):
+cl = Cluster(sph.Settings(numParticles=n), world=3, devices=[0, 0, 0], capacity=n + 1024, ghost_capacity=n + 2,
+             emig_capacity=n, rebalance_every=3)
+for i, idx in enumerate(partition(pos, 0.1, slab_ranges(100, 3))):
+    cl.load(i, pos[idx], vel[idx], idx.astype(np.uint32))
+cl.advance(6)
+for _ in range(4):
     cl.step()
-import ctypes as C
-for b in backends:
-    f, c = C.c_uint32(), C.c_int()
-    b.N.check(b.lib.sph_debug_flags(b.h, C.byref(f), C.byref(c)))
-    print("slab flags", f.value)
-    total |= f.value
-    b.close()
+cl.sync()
+for i in range(3):
+    st = cl.stats(i)
+    assert st["checked_build"], "not the self-checking build"
+    print("slab flags", st["debug_flags"])
+    total |= st["debug_flags"]
+cl.close()
 print("CHECKED_BUILD_FLAGS", total)

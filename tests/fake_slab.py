@@ -1,10 +1,10 @@
-"""CPU stand-in for the slab-mode library (same buffers, same call protocol as
-cudafluidsimulator_b200.slab.SlabBackend), built on the CPU oracle.  Lets the halo /
+"""CPU stand-in for a slab of the multi-GPU decomposition (the buffers and the call protocol
+tests/slab_model.py drives), built on the CPU oracle.  Lets the halo /
 migration protocol of SlabDriver run under gloo without a GPU.  Test infrastructure."""
 import numpy as np
 import torch
 
-from cudafluidsimulator_b200.slab import SlabInfo
+from slab_model import SlabInfo
 from oracle.oracle import CpuOracle
 
 DEAD = np.uint32(0xFFFFFFFF)

@@ -218,20 +218,29 @@ def test_timed_step_fills_reference_buckets():
 
 
 def test_mouse_push_matches_oracle():
+    """The velocity increment of a click (+-2.5 / +-5 per axis, ref: simulator.cu:347-364) per
+    particle, isolated by running the same step with and without the push: equal to the oracle's
+    increment to 1e-5 (a missed or doubled half-push would be off by >= 2.5)."""
     pos, vel = random_state(40000, seed=13, lo=3.0, hi=7.0)
     o = CpuOracle(len(pos))
     o.set_state(pos, vel)
     o.step()
+    v_before = o.vel.copy()
     o.push(pos, 400, 300)          # grid of the PRE-step positions (SURVEY Appendix B)
-    sim = make(len(pos))
-    sim.set_state(pos, vel)
-    sim.simulate()
-    sim.moveParticles((400, 300))
-    p1, v1 = sim.get_state()
-    pushed = np.any(np.abs(o.vel - v1) > 1.0, axis=1)
-    assert not pushed.any(), f"{pushed.sum()} particles pushed differently"
-    assert (np.abs(o.vel[:, 2]) > 4).sum() > 0  # the push actually hit something
-    sim.close()
+    d_oracle = o.vel - v_before
+    out = []
+    for push in (False, True):
+        sim = make(len(pos))
+        sim.set_state(pos, vel)
+        sim.simulate()
+        if push:
+            sim.moveParticles((400, 300))
+        out.append(sim.get_state()[1])
+        sim.close()
+    np.testing.assert_allclose(out[1] - out[0], d_oracle, rtol=0, atol=1e-5)
+    assert (np.abs(d_oracle[:, 2]) > 4).sum() > 0 and (np.abs(d_oracle[:, 0]) > 2).sum() > 0   # it hit something
+    # and the pushed state itself, within the single-step velocity tolerance
+    np.testing.assert_allclose(out[1], o.vel, rtol=1e-5, atol=1e-4)
 
 
 def test_scaled_domain_256_cells():
@@ -307,6 +316,46 @@ def test_16m_developed_subdomain_matches_oracle():
     np.testing.assert_allclose(rho[sub][inner], orho[inner], rtol=2e-6, atol=0)
     np.testing.assert_allclose(prs[sub][inner], oprs[inner], rtol=0, atol=2e-6 * float(orho.max()))
     # forces from the full-domain density of the same particles (ours), oracle arithmetic
+    of = o.forces(pos[sub], vel[sub], rho[sub], prs[sub])
+    tol = force_tolerance(o, pos[sub], vel[sub], rho[sub], prs[sub], rel=RTOL_F)
+    err = np.abs(f[sub] - of)
+    assert np.all(err[inner] <= tol[inner]), f"force: worst excess {np.max(err[inner] / tol[inner]):.3g}x"
+    o.step()
+    np.testing.assert_allclose(p1[sub][inner], o.pos[inner], rtol=RTOL_POS, atol=2e-6)
+
+
+def test_1m_random_developed_subdomain_matches_oracle():
+    """BASELINE config 2 at its full size (1 M particles, glibc rand() seed 1, reference box),
+    developed for 60 steps (the cloud has fallen 1.8 units: a dense layer on the floor under a
+    sparse gas).  Same closed sub-problem argument as the 16 M test: a floor sub-domain plus a
+    2.5 h halo re-solved by the oracle."""
+    import ctypes
+    n = 1_000_000
+    ctypes.CDLL("libc.so.6").srand(1)
+    s = sph.Settings(numParticles=n, randomInit=True)
+    sim = sph.Simulator(s, record_force=True)
+    sim.setup()
+    sim.advance(60)
+    pos, vel = sim.get_state()
+    K, Cn = sim.get_neighbor_counts()
+    sim.simulate()
+    rho, prs, f = sim.get_density_pressure_force()
+    p1, _ = sim.get_state()
+    sim.close()
+
+    lo = np.float32([4.0, 0.0, 4.0]); hi = np.float32([5.0, 0.8, 5.0])
+    halo = np.float32(0.25)
+    sub = np.flatnonzero(np.all((pos >= lo - halo) & (pos < hi + halo), axis=1))
+    inner = np.all((pos[sub] >= lo) & (pos[sub] < hi), axis=1)
+    assert inner.sum() > 2000 and len(sub) < 200_000
+    o = CpuOracle(len(sub))
+    o.set_state(pos[sub], vel[sub])
+    orho, oprs, oK, oC = o.density()
+    np.testing.assert_array_equal(K[sub][inner], oK[inner])
+    np.testing.assert_array_equal(Cn[sub][inner], oC[inner])
+    assert oK[inner].max() > 40                      # the dense floor layer is in the sample
+    np.testing.assert_allclose(rho[sub][inner], orho[inner], rtol=RTOL_RHO, atol=0)
+    np.testing.assert_allclose(prs[sub][inner], oprs[inner], rtol=0, atol=RTOL_RHO * float(orho.max()))
     of = o.forces(pos[sub], vel[sub], rho[sub], prs[sub])
     tol = force_tolerance(o, pos[sub], vel[sub], rho[sub], prs[sub], rel=RTOL_F)
     err = np.abs(f[sub] - of)

@@ -120,21 +120,31 @@ def test_100_step_aggregates_vs_reference(n, random_init):
 
 
 def test_mouse_push_vs_reference():
+    """Click increments against the reference's own kernelMoveParticles, isolated by differencing a
+    step with and a step without the click on both sides: 1e-5."""
     pos, vel = random_state(40000, seed=13, lo=3.0, hi=7.0)
-    ref = RefSim(len(pos))
-    ref.set_state(pos, vel)
-    ref.step_click(400, 300)
-    r = ref.get_state()
-    ref.close()
-    sim = sph.Simulator(sph.Settings(numParticles=len(pos)))
-    sim.setup()
-    sim.set_state(pos, vel)
-    sim.simulate()
-    sim.moveParticles((400, 300))
-    p1, v1 = sim.get_state()
-    sim.close()
-    assert not np.any(np.abs(r["vel"] - v1) > 1.0)
-    assert (np.abs(r["vel"][:, 2]) > 4).sum() > 0
+    r = []
+    for click in (False, True):
+        ref = RefSim(len(pos))
+        ref.set_state(pos, vel)
+        if click:
+            ref.step_click(400, 300)
+        else:
+            ref.step()
+        r.append(ref.get_state()["vel"])
+        ref.close()
+    out = []
+    for click in (False, True):
+        sim = sph.Simulator(sph.Settings(numParticles=len(pos)))
+        sim.setup()
+        sim.set_state(pos, vel)
+        sim.simulate()
+        if click:
+            sim.moveParticles((400, 300))
+        out.append(sim.get_state()[1])
+        sim.close()
+    np.testing.assert_allclose(out[1] - out[0], r[1] - r[0], rtol=0, atol=1e-5)
+    assert (np.abs(r[1] - r[0])[:, 2] > 4).sum() > 0
 
 
 @pytest.mark.parametrize("morton", [False, True], ids=["index_sort", "z_index_sort"])

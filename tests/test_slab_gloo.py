@@ -1,7 +1,8 @@
-"""CPU suite, world_size 2 over gloo: the slab driver's halo-exchange / migration
-protocol (cudafluidsimulator_b200/slab.py) with a CPU stand-in for the library, compared
-with the undecomposed CPU oracle.  The GPU kernels of slab mode are covered by
-tests/test_gpu_slab.py on a multi-GPU box."""
+"""CPU suite, world sizes 2 and 3 over gloo: the slab decomposition -- layer ranges, particle
+partition, ghost halo exchanges A and B, migration -- as a Python model (tests/slab_model.py) with a
+CPU stand-in for the library (tests/fake_slab.py), compared with the undecomposed CPU oracle.  The
+product's protocol is C++/CUDA (csrc/sph_cluster.cu) and is covered on GPUs by
+tests/test_gpu_cluster.py: several slabs on one GPU, peer-to-peer copies and NCCL on two."""
 import os
 import socket
 
@@ -12,7 +13,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import random_state
-from cudafluidsimulator_b200.slab import SlabDriver, partition, slab_ranges
+from cudafluidsimulator_b200.cluster import partition, slab_ranges
+from slab_model import SlabDriver
 
 
 def test_slab_ranges_cover_and_balance():
