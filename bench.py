@@ -333,7 +333,8 @@ def run_cluster(args, wl, rank, local_rank, world):
                       boxDim=wl["boxDim"], numCellsPerDim=wl["numCellsPerDim"])
     # a cell layer (0.1) holds one or two lattice planes (0.09 apart); the capacities leave room for more
     plane = int(np.ceil(n_max / max(1.0, (0.1 * nz / world) / 0.09)))
-    caps = dict(capacity=int(n_max * 1.15) + 65536, ghost_capacity=5 * plane + 16384, emig_capacity=3 * plane + 16384)
+    # (a boundary layer holds at most two planes, and at most one plane crosses a face in a step)
+    caps = dict(capacity=int(n_max * 1.15) + 65536, ghost_capacity=3 * plane + 16384, emig_capacity=2 * plane + 16384)
 
     def make():
         cl = Cluster(st, world=world, rank=rank, devices=[local_rank], nz_cells=nz, nccl_id=fresh_id(),

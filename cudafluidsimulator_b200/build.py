@@ -66,7 +66,7 @@ def build_library(force: bool = False, verbose_ptxas: bool = False, checked: boo
         if checked:
             flags.append("-DSPH_BOUNDS_CHECK")
         # libdl: NCCL is resolved with dlopen when a multi-process cluster is created (sph_cluster.cu)
-        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", target, *[CSRC / f for f in CU_SOURCES], "-ldl"])
+        _run([_nvcc(), *flags, "-I", INCLUDE, "-o", target, *[CSRC / f for f in CU_SOURCES], "-ldl", "-lpthread"])
     return target
 
 

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "sph_internal.cuh"
@@ -655,7 +656,7 @@ int sph_cluster_step(sph_cluster *c) {
         CU(cudaSetDevice(s.device));
         if (!s.out_stage) {
             CU(cudaMalloc(&s.out_stage, (size_t)c->cap * sizeof(float4)));
-            CU(cudaMallocHost(&s.host_records, (size_t)c->cap * sizeof(float4)));
+            if (!s.host_records) CU(cudaMallocHost(&s.host_records, (size_t)c->cap * sizeof(float4)));
             CU(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&s.ev_out_ready, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.ev_out_done, cudaEventDisableTiming));
@@ -712,25 +713,42 @@ int sph_cluster_download(sph_cluster *c, int li, uint32_t *ids, float *pos, floa
     return 0;
 }
 
+// getPosition() of the multi-GPU path: every local slab's records {x, y, z, id} come to its pinned
+// host buffer (one asynchronous copy per slab, all in flight together), then one host thread per
+// slab scatters them into out[3 * id ...] (ids are disjoint between slabs).
 int sph_cluster_positions(sph_cluster *c, float *out, int64_t n_global) {
     if (!c || !out) return sph_internal_fail(SPH_E_INVALID, "bad argument");
     int rc = sync_all(c);
     if (rc) return rc;
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
+        if (!s.host_records) CU(cudaMallocHost(&s.host_records, (size_t)c->cap * sizeof(float4)));
         const int n = s.dyn_host->n_total;
-        std::vector<float4> hp((size_t)std::max(n, 1));
-        if (n) CU(cudaMemcpy(hp.data(), s.core.d->cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < n; ++i) {
-            uint32_t id;
-            memcpy(&id, &hp[i].w, 4);
-            if (id == 0xffffffffu) continue;
-            if ((int64_t)id >= n_global) return sph_internal_fail(SPH_E_STATE, "slab %d holds id %u >= %lld", s.rank, id, (long long)n_global);
-            out[3 * (size_t)id] = hp[i].x;
-            out[3 * (size_t)id + 1] = hp[i].y;
-            out[3 * (size_t)id + 2] = hp[i].z;
-        }
+        if (n) CU(cudaMemcpyAsync(s.host_records, s.core.d->cur_pos, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s.core.stream));
     }
+    std::vector<std::thread> workers;
+    std::vector<long long> bad(c->slabs.size(), -1);
+    for (size_t i = 0; i < c->slabs.size(); ++i) {
+        Slab &s = c->slabs[i];
+        CU(cudaSetDevice(s.device));
+        CU(cudaStreamSynchronize(s.core.stream));
+        workers.emplace_back([&s, &bad, i, out, n_global]() {
+            const int n = s.dyn_host->n_total;
+            const float4 *hp = s.host_records;
+            for (int k = 0; k < n; ++k) {
+                uint32_t id;
+                memcpy(&id, &hp[k].w, 4);
+                if (id == 0xffffffffu) continue;   // emigrated
+                if ((int64_t)id >= n_global) { bad[i] = id; return; }
+                out[3 * (size_t)id] = hp[k].x;
+                out[3 * (size_t)id + 1] = hp[k].y;
+                out[3 * (size_t)id + 2] = hp[k].z;
+            }
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (size_t i = 0; i < bad.size(); ++i)
+        if (bad[i] >= 0) return sph_internal_fail(SPH_E_STATE, "slab %d holds id %lld >= %lld", c->slabs[i].rank, bad[i], (long long)n_global);
     return 0;
 }
 
