@@ -272,8 +272,8 @@ def cluster_parity_check(world, rank, local_rank, nccl_id_fn, gather):
     cl.load(0, pos[mine], vel[mine], ids[mine])
     cl.advance(steps)
     s = cl.stats(0)
-    cl.close()
     parts = gather((s["kinetic_energy"], s["density_sum"], s["n_owned"], s["migrated_total"]))
+    cl.close()
     if rank != 0:
         return None
     ke = sum(q[0] for q in parts)
@@ -434,7 +434,9 @@ def run_cluster(args, wl, rank, local_rank, world):
                             f"id-hashed uniform z-component of std {args.sigma}: every slab face is crossed in both "
                             "directions from the first steps on",
                     "parallelism": f"{world} z-slabs, one process per GPU; ghost halo exchange (pos/vel, then pressure "
-                                   "terms) + particle migration per step inside libsph_b200.so over ncclSend/ncclRecv, "
+                                   "terms) + particle migration per step inside libsph_b200.so: the receiving kernels read "
+                                   "the neighbour's message buffers in place over NVLink (CUDA IPC peer memory, seq/ack "
+                                   "flags in the message headers; SPH_CLUSTER_NCCL_DATA=1: ncclSend/ncclRecv instead), "
                                    "counts device-resident (no host round trip inside a step); slab boundaries "
                                    f"rebalanced every {args.rebalance_every} steps",
                     "l2": f"state evolves step to step; working set {n * 124 / 1e6:.0f} MB per GPU vs 126 MB L2"},

@@ -17,9 +17,17 @@
 //   [migration] emigrants -> appended behind the neighbour's particles, keyed
 //
 // Every count (particles, boundary layers, ghosts, emigrants) stays in device memory (SlabDyn and
-// the message headers); kernels are launched over capacities.  A message is a fixed-capacity
-// buffer moved whole: between slabs of this process with cudaMemcpyPeerAsync (NVLink P2P, ordered
-// by events), between processes with ncclSend / ncclRecv on the slab's stream.
+// the message headers); kernels are launched over capacities.  How a message reaches the neighbour:
+//   * slabs of this process: cudaMemcpyPeerAsync of the fixed-capacity buffer (NVLink P2P),
+//     ordered by events;
+//   * slabs of different processes (one process per GPU): the RECEIVER's unpack kernel reads the
+//     sender's buffer in place over NVLink -- the buffers are mapped into the neighbour with CUDA
+//     IPC at creation -- so exactly `count` entries cross the link and nothing is staged.  Sender
+//     and receiver hand-shake on two words of the message header (seq: "round r is complete",
+//     ack: "round r has been consumed"), written and polled by one-thread kernels on the slabs'
+//     own streams: the transfer is fused into the unpack kernels and the host never waits.
+//     NCCL only carries the IPC handles and the rebalancing numbers.  SPH_CLUSTER_NCCL_DATA=1
+//     moves the messages with ncclSend / ncclRecv instead (whole buffers; the A/B comparison).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -97,6 +105,12 @@ int load_nccl() {
     } while (0)
 
 enum MsgKind { kHaloA = 0, kHaloB = 1, kMigrate = 2, kMsgKinds = 3 };
+// phases of a step, for SPH_CLUSTER_TRACE (device time between CUDA events on the slab's stream)
+enum Phase { kPhSort = 0, kPhPackA, kPhDensityIn, kPhGhostsIn, kPhDensityBd, kPhPackB, kPhForceIn, kPhPressuresIn,
+             kPhForceBd, kPhMigrate, kPhases };
+const char *kPhaseNames[kPhases] = {"sort+reorder", "pack halo A", "density (interior)", "wait + ghosts in",
+                                    "density (boundary)", "pack halo B", "force (interior)", "wait + pressures in",
+                                    "force (boundary)", "wait + immigrants in"};
 
 struct Slab {
     sph_sim *sim = nullptr;
@@ -108,6 +122,8 @@ struct Slab {
     // messages: [kind][side]; side 0 = towards / from the slab below, 1 = above
     MsgHeader *send[kMsgKinds][2] = {};
     MsgHeader *recv[kMsgKinds][2] = {};
+    MsgHeader *remote[kMsgKinds][2] = {};      // the send buffer of a neighbour in ANOTHER process that faces
+                                               // this slab, mapped with CUDA IPC (peer memory)
     cudaEvent_t ev_packed[kMsgKinds] = {};     // this slab's send buffers of that kind are complete
     cudaEvent_t ev_copied[kMsgKinds][2] = {};  // this slab has copied the message of its neighbour on that side
     bool copied_pending[kMsgKinds][2] = {};    // ... and that neighbour has not waited for it yet
@@ -125,6 +141,10 @@ struct Slab {
     double *stats_dev = nullptr;   // 2 doubles
     int *info_dev = nullptr;       // 3 x 8 ints: rebalancing numbers of this slab / from below / from above
     bool hashed = false;
+    // SPH_CLUSTER_TRACE=1: CUDA events at the phase boundaries of every step
+    std::vector<cudaEvent_t> trace_ev;
+    size_t trace_used = 0;
+    double phase_ms[kPhases] = {};
 };
 
 }  // namespace
@@ -141,6 +161,9 @@ struct sph_cluster {
     int64_t launches = 0;
     int steps_since_rebalance = 0;
     bool loaded = false;
+    bool trace = false;                 // SPH_CLUSTER_TRACE
+    bool peer_mem = false;              // messages between processes are read in place over NVLink
+    uint32_t round[kMsgKinds] = {1, 1, 1};   // exchange rounds so far + 1, per message kind (same on every process)
 };
 
 namespace {
@@ -191,10 +214,6 @@ int exchange(sph_cluster *c, int kind) {
     const size_t bytes = c->msg_bytes[kind];
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
-        CU(cudaEventRecord(s.ev_packed[kind], s.core.stream));
-    }
-    for (Slab &s : c->slabs) {
-        CU(cudaSetDevice(s.device));
         bool grouped = false;
         for (int side = 0; side < 2; ++side) {
             const int peer = side ? s.rank + 1 : s.rank - 1;
@@ -207,17 +226,18 @@ int exchange(sph_cluster *c, int kind) {
                                        s.core.stream));
                 CU(cudaEventRecord(s.ev_copied[kind][side], s.core.stream));
                 s.copied_pending[kind][side] = true;
-            } else {
+            } else if (!c->peer_mem) {
                 if (!grouped) {
                     NC(g_nccl.GroupStart());
                     grouped = true;
                 }
                 NC(g_nccl.Send(s.send[kind][side], bytes, ncclChar, peer, s.comm, s.core.stream));
                 NC(g_nccl.Recv(s.recv[kind][side], bytes, ncclChar, peer, s.comm, s.core.stream));
-            }
+            }   // (peer memory: nothing to move, the unpack kernels read the neighbour's buffer)
         }
         if (grouped) NC(g_nccl.GroupEnd());
     }
+    c->round[kind] += 1;
     return 0;
 }
 
@@ -236,9 +256,65 @@ int wait_taken(sph_cluster *c, Slab &s, int kind) {
     return 0;
 }
 
-MsgHeader *msg_or_null(const sph_cluster *c, const Slab &s, MsgHeader *m, int side) {
+bool has_peer(const sph_cluster *c, const Slab &s, int side) {
     const int peer = side ? s.rank + 1 : s.rank - 1;
-    return (peer < 0 || peer >= c->opt.world) ? nullptr : m;
+    return peer >= 0 && peer < c->opt.world;
+}
+bool peer_is_remote_mem(const sph_cluster *c, const Slab &s, int side) {
+    const int peer = side ? s.rank + 1 : s.rank - 1;
+    return has_peer(c, s, side) && !is_local(c, peer) && c->peer_mem;
+}
+// send buffer of `kind` towards `side`, or null without a neighbour there
+MsgHeader *out_msg(const sph_cluster *c, const Slab &s, int kind, int side) {
+    return has_peer(c, s, side) ? s.send[kind][side] : nullptr;
+}
+// where the unpack kernels find the neighbour's message: the local copy, or the neighbour's own
+// buffer (peer memory); null without a neighbour
+MsgHeader *in_msg(const sph_cluster *c, const Slab &s, int kind, int side) {
+    if (!has_peer(c, s, side)) return nullptr;
+    return peer_is_remote_mem(c, s, side) ? s.remote[kind][side] : s.recv[kind][side];
+}
+// the hand-shake (no-ops unless the neighbour on that side is reached through peer memory)
+void before_pack(sph_cluster *c, Slab &s, int kind) {   // the previous round of my buffers has been consumed
+    launch_msg_flags(kWaitAck, peer_is_remote_mem(c, s, 0) ? s.send[kind][0] : nullptr,
+                     peer_is_remote_mem(c, s, 1) ? s.send[kind][1] : nullptr, c->round[kind] - 1, s.core.stream);
+}
+void after_pack(sph_cluster *c, Slab &s, int kind) {    // this round of my buffers is complete
+    cudaEventRecord(s.ev_packed[kind], s.core.stream);  // (what a neighbour in this process waits for)
+    launch_msg_flags(kSetSeq, peer_is_remote_mem(c, s, 0) ? s.send[kind][0] : nullptr,
+                     peer_is_remote_mem(c, s, 1) ? s.send[kind][1] : nullptr, c->round[kind], s.core.stream);
+}
+void before_unpack(sph_cluster *c, Slab &s, int kind, uint32_t round) {   // the neighbours' round is complete
+    launch_msg_flags(kWaitSeq, peer_is_remote_mem(c, s, 0) ? s.remote[kind][0] : nullptr,
+                     peer_is_remote_mem(c, s, 1) ? s.remote[kind][1] : nullptr, round, s.core.stream);
+}
+void after_unpack(sph_cluster *c, Slab &s, int kind, uint32_t round) {    // ... and I have consumed it
+    launch_msg_flags(kSetAck, peer_is_remote_mem(c, s, 0) ? s.remote[kind][0] : nullptr,
+                     peer_is_remote_mem(c, s, 1) ? s.remote[kind][1] : nullptr, round, s.core.stream);
+}
+
+// SPH_CLUSTER_TRACE: an event on the slab's stream; consecutive events bracket the phases of a step
+int mark(sph_cluster *c, Slab &s) {
+    if (!c->trace) return 0;
+    if (s.trace_used == s.trace_ev.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        s.trace_ev.push_back(e);
+    }
+    CU(cudaEventRecord(s.trace_ev[s.trace_used++], s.core.stream));
+    return 0;
+}
+void collect_trace(sph_cluster *c) {   // after the streams are synchronised
+    if (!c->trace) return;
+    for (Slab &s : c->slabs) {
+        cudaSetDevice(s.device);
+        for (size_t i = 0; i + kPhases < s.trace_used; i += kPhases + 1)   // kPhases + 1 events per step
+            for (int ph = 0; ph < kPhases; ++ph) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, s.trace_ev[i + ph], s.trace_ev[i + ph + 1]) == cudaSuccess) s.phase_ms[ph] += ms;
+            }
+        s.trace_used = 0;
+    }
 }
 
 // Launch parameters of a slab: counts come from SlabDyn, the host only knows the capacity.
@@ -246,15 +322,26 @@ Params launch_params(const Slab &s, int cap) {
     Params p = *s.core.p;
     p.n = p.n_owned = cap;
     p.dyn = s.dyn;
-    p.cta_gap_at = p.cta_gap_len = p.cta_count = 0;
+    p.part = p.part_ctas = p.cta_count = 0;
     p.slot_begin = 0;
     p.slot_end = cap + 2 * s.core.ghost_cap;
     return p;
 }
 
+// The neighbour kernels in two parts: the interior CTAs, which read no ghost data, are enqueued
+// BEFORE the stream waits for the neighbours' message, the boundary CTAs after it.  By the time
+// the stream reaches the wait, the message has long arrived: the exchange costs no time.
+Params part_params(const sph_cluster *c, const Slab &s, int part) {
+    Params p = launch_params(s, c->cap);
+    p.part = part;
+    p.part_ctas = (c->cap_g + kBlock - 1) / kBlock + 1;   // CTAs a boundary layer can touch
+    if (part == 2) p.cta_count = 2 * p.part_ctas;
+    return p;
+}
+
 int enqueue_step(sph_cluster *c) {
     const int cap = c->cap;
-    // -- build: sort, reorder, pack the boundary layers ---------------------------------------
+    // -- build: sort, reorder, pack the boundary layers; density of the interior -------------------
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
         const Params p = launch_params(s, cap);
@@ -265,58 +352,83 @@ int enqueue_step(sph_cluster *c) {
             s.hashed = true;
             c->launches += 1;
         }
+        mark(c, s);
         *s.core.sorted_buf = sort_pairs_async(d.key, d.pairs[0], d.pairs[1], cap, *s.core.passes, d.sort_scratch,
                                               s.core.sm_count, st, nullptr, &s.dyn->n_total);
         d.sorted_pairs = d.pairs[*s.core.sorted_buf];
         launch_reorder(p, d, *s.core.sorted_buf, cap, s.core.sm_count, st);
+        mark(c, s);
         int rc = wait_taken(c, s, kHaloA);
         if (rc) return rc;
-        launch_pack_layer(p, d, false, msg_or_null(c, s, s.send[kHaloA][0], 0), msg_or_null(c, s, s.send[kHaloA][1], 1),
-                          c->cap_g, s.dyn, st);
-        c->launches += 3 + *s.core.passes;
+        before_pack(c, s, kHaloA);
+        launch_pack_layer(p, d, false, out_msg(c, s, kHaloA, 0), out_msg(c, s, kHaloA, 1), c->cap_g, s.dyn, st);
+        after_pack(c, s, kHaloA);
+        mark(c, s);
+        launch_density(part_params(c, s, 1), *s.core.th, d, false, st);
+        mark(c, s);
+        c->launches += 4 + *s.core.passes;
     }
+    const uint32_t round_a = c->round[kHaloA];
     int rc = exchange(c, kHaloA);
     if (rc) return rc;
-    // -- ghosts in, density, pack {p, a} -------------------------------------------------------
+    // -- ghosts in, density of the boundary layers, pack {p, a}; force of the interior -------------
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
         const Params p = launch_params(s, cap);
         DeviceState &d = *s.core.d;
         cudaStream_t st = s.core.stream;
+        before_unpack(c, s, kHaloA, round_a);
         for (int side = 0; side < 2; ++side)
-            launch_ghost_install(p, d, msg_or_null(c, s, s.recv[kHaloA][side], side), c->cap_g, side, s.dyn, st);
-        launch_density(p, *s.core.th, d, false, st);
+            launch_ghost_install(p, d, in_msg(c, s, kHaloA, side), c->cap_g, side, s.dyn, st);
+        after_unpack(c, s, kHaloA, round_a);
+        mark(c, s);
+        launch_density(part_params(c, s, 2), *s.core.th, d, false, st);
+        mark(c, s);
         rc = wait_taken(c, s, kHaloB);
         if (rc) return rc;
-        launch_pack_layer(p, d, true, msg_or_null(c, s, s.send[kHaloB][0], 0), msg_or_null(c, s, s.send[kHaloB][1], 1),
-                          c->cap_g, s.dyn, st);
-        c->launches += 4;
+        before_pack(c, s, kHaloB);
+        launch_pack_layer(p, d, true, out_msg(c, s, kHaloB, 0), out_msg(c, s, kHaloB, 1), c->cap_g, s.dyn, st);
+        after_pack(c, s, kHaloB);
+        mark(c, s);
+        // (emigrants of either force launch go straight into the migration messages)
+        rc = wait_taken(c, s, kMigrate);
+        if (rc) return rc;
+        before_pack(c, s, kMigrate);
+        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(&s.send[kMigrate][side]->count, 0, sizeof(uint32_t), st));
+        launch_force_integrate(part_params(c, s, 1), *s.core.th, d, st);
+        mark(c, s);
+        c->launches += 6;
     }
+    const uint32_t round_b = c->round[kHaloB];
     rc = exchange(c, kHaloB);
     if (rc) return rc;
-    // -- ghost pressures in, force + integrate (emigrants into the migration messages) ---------
+    // -- ghost pressures in, force + integrate of the boundary layers ------------------------------
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
         const Params p = launch_params(s, cap);
         DeviceState &d = *s.core.d;
         cudaStream_t st = s.core.stream;
-        launch_ghost_pa(p, d, msg_or_null(c, s, s.recv[kHaloB][0], 0), msg_or_null(c, s, s.recv[kHaloB][1], 1),
-                        c->cap_g, st);
-        rc = wait_taken(c, s, kMigrate);
-        if (rc) return rc;
-        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(s.send[kMigrate][side], 0, sizeof(MsgHeader), st));
-        launch_force_integrate(p, *s.core.th, d, st);
+        before_unpack(c, s, kHaloB, round_b);
+        launch_ghost_pa(p, d, in_msg(c, s, kHaloB, 0), in_msg(c, s, kHaloB, 1), c->cap_g, st);
+        after_unpack(c, s, kHaloB, round_b);
+        mark(c, s);
+        launch_force_integrate(part_params(c, s, 2), *s.core.th, d, st);
+        after_pack(c, s, kMigrate);
+        mark(c, s);
         c->launches += 2;
     }
+    const uint32_t round_m = c->round[kMigrate];
     rc = exchange(c, kMigrate);
     if (rc) return rc;
     // -- immigrants appended, counts of the next step --------------------------------------------
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
         const Params p = launch_params(s, cap);
-        launch_append_immigrants(p, *s.core.d, msg_or_null(c, s, s.recv[kMigrate][0], 0),
-                                 msg_or_null(c, s, s.recv[kMigrate][1], 1), c->cap_m, s.send[kMigrate][0],
-                                 s.send[kMigrate][1], cap, s.dyn, false, s.core.stream);
+        before_unpack(c, s, kMigrate, round_m);
+        launch_append_immigrants(p, *s.core.d, in_msg(c, s, kMigrate, 0), in_msg(c, s, kMigrate, 1), c->cap_m,
+                                 s.send[kMigrate][0], s.send[kMigrate][1], cap, s.dyn, false, s.core.stream);
+        after_unpack(c, s, kMigrate, round_m);
+        mark(c, s);
         CU(cudaMemcpyAsync(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, s.core.stream));
         c->launches += 2;
     }
@@ -332,6 +444,7 @@ int sync_all(sph_cluster *c) {
         CU(cudaGetLastError());
         s.out_pending = false;
         s.known_total = s.dyn_host->n_total;
+        if (c->trace && &s == &c->slabs.back()) collect_trace(c);
         if (s.dyn_host->overflow)
             return sph_internal_fail(SPH_E_STATE,
                                      "slab %d: capacity exceeded (flags %u: 1 = particles, 2 = ghost layer, 4 = emigrants "
@@ -469,6 +582,49 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
             if (r != ncclSuccess) rc = sph_internal_fail(SPH_E_STATE, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
         }
     }
+    // Messages between processes: map the neighbours' send buffers (CUDA IPC) so that the unpack
+    // kernels read them in place.  The handles travel over the NCCL communicator.
+    const char *tr = getenv("SPH_CLUSTER_TRACE");
+    c->trace = tr && atoi(tr) != 0;
+    const char *force_nccl = getenv("SPH_CLUSTER_NCCL_DATA");
+    c->peer_mem = need_nccl && !(force_nccl && atoi(force_nccl) != 0);
+    for (size_t i = 0; i < c->slabs.size() && rc == 0 && c->peer_mem; ++i) {
+        Slab &s = c->slabs[i];
+        struct Handles { cudaIpcMemHandle_t h[kMsgKinds]; };
+        Handles mine[2], theirs[2];
+        Handles *dev = nullptr;
+        auto fail_cuda = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) rc = sph_internal_fail((int)e, "CUDA IPC set-up failed: %s", cudaGetErrorString(e)); };
+        fail_cuda(cudaSetDevice(s.device));
+        fail_cuda(cudaMalloc(&dev, 4 * sizeof(Handles)));
+        bool any = false;
+        for (int side = 0; side < 2 && rc == 0; ++side) {
+            const int peer = side ? s.rank + 1 : s.rank - 1;
+            if (peer < 0 || peer >= o->world || is_local(c, peer)) continue;
+            for (int k = 0; k < kMsgKinds; ++k) fail_cuda(cudaIpcGetMemHandle(&mine[side].h[k], s.send[k][side]));
+            any = true;
+        }
+        if (rc == 0 && any) {
+            fail_cuda(cudaMemcpy(dev, mine, 2 * sizeof(Handles), cudaMemcpyHostToDevice));
+            ncclResult_t r = g_nccl.GroupStart();
+            for (int side = 0; side < 2 && r == ncclSuccess; ++side) {
+                const int peer = side ? s.rank + 1 : s.rank - 1;
+                if (peer < 0 || peer >= o->world || is_local(c, peer)) continue;
+                r = g_nccl.Send(dev + side, sizeof(Handles), ncclChar, peer, s.comm, s.core.stream);
+                if (r == ncclSuccess) r = g_nccl.Recv(dev + 2 + side, sizeof(Handles), ncclChar, peer, s.comm, s.core.stream);
+            }
+            if (r == ncclSuccess) r = g_nccl.GroupEnd();
+            if (r != ncclSuccess) rc = sph_internal_fail(SPH_E_STATE, "exchange of the IPC handles failed: %s", g_nccl.GetErrorString(r));
+            fail_cuda(cudaStreamSynchronize(s.core.stream));
+            fail_cuda(cudaMemcpy(theirs, dev + 2, 2 * sizeof(Handles), cudaMemcpyDeviceToHost));
+            for (int side = 0; side < 2 && rc == 0; ++side) {
+                const int peer = side ? s.rank + 1 : s.rank - 1;
+                if (peer < 0 || peer >= o->world || is_local(c, peer)) continue;
+                for (int k = 0; k < kMsgKinds; ++k)
+                    fail_cuda(cudaIpcOpenMemHandle((void **)&s.remote[k][side], theirs[side].h[k], cudaIpcMemLazyEnablePeerAccess));
+            }
+        }
+        cudaFree(dev);
+    }
     // peer access between the devices of local neighbours (NVLink P2P); a failure only means the
     // copies are staged by the driver
     for (size_t i = 0; i + 1 < c->slabs.size() && rc == 0; ++i) {
@@ -492,6 +648,39 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
 
 void sph_cluster_destroy(sph_cluster *c) {
     if (!c) return;
+    // Peer memory: a neighbour in another process may still be reading this slab's buffers (and this
+    // slab the neighbour's).  Drain the own streams, then swap one word with every remote neighbour
+    // -- it sends only after ITS streams have drained -- before anything is unmapped or freed.
+    if (c->peer_mem) {
+        for (Slab &s : c->slabs) {
+            cudaSetDevice(s.device);
+            if (s.core.stream) cudaStreamSynchronize(s.core.stream);
+        }
+        for (Slab &s : c->slabs) {
+            if (!s.comm || !s.info_dev) continue;
+            cudaSetDevice(s.device);
+            bool grouped = false;
+            for (int side = 0; side < 2; ++side) {
+                const int peer = side ? s.rank + 1 : s.rank - 1;
+                if (peer < 0 || peer >= c->opt.world || is_local(c, peer)) continue;
+                if (!grouped) { g_nccl.GroupStart(); grouped = true; }
+                g_nccl.Send(s.info_dev, 4, ncclChar, peer, s.comm, s.core.stream);
+                g_nccl.Recv(s.info_dev + 8 * (1 + side), 4, ncclChar, peer, s.comm, s.core.stream);
+            }
+            if (grouped) {
+                g_nccl.GroupEnd();
+                cudaStreamSynchronize(s.core.stream);
+            }
+        }
+    }
+    if (c->trace)
+        for (Slab &s : c->slabs) {
+            const int steps = std::max(1, s.dyn_host ? s.dyn_host->steps : 1);
+            fprintf(stderr, "[sph cluster trace] slab %d, ms per step over %d steps:", s.rank, steps);
+            for (int ph = 0; ph < kPhases; ++ph) fprintf(stderr, " %s %.3f;", kPhaseNames[ph], s.phase_ms[ph] / steps);
+            fprintf(stderr, "\n");
+            for (cudaEvent_t e : s.trace_ev) cudaEventDestroy(e);
+        }
     for (Slab &s : c->slabs) {
         cudaSetDevice(s.device);
         if (s.core.stream) cudaStreamSynchronize(s.core.stream);
@@ -510,6 +699,7 @@ void sph_cluster_destroy(sph_cluster *c) {
         }
         for (int k = 0; k < kMsgKinds; ++k) {
             for (int side = 0; side < 2; ++side) {
+                if (s.remote[k][side]) cudaIpcCloseMemHandle(s.remote[k][side]);
                 cudaFree(s.send[k][side]);
                 cudaFree(s.recv[k][side]);
                 if (s.ev_copied[k][side]) cudaEventDestroy(s.ev_copied[k][side]);
@@ -545,9 +735,9 @@ int sph_cluster_load(sph_cluster *c, int li, int n, const float *pos, const floa
     s.known_total = n;
     s.hashed = false;
     for (int k = 0; k < kMsgKinds; ++k)
-        for (int side = 0; side < 2; ++side) {
-            CU(cudaMemset(s.send[k][side], 0, sizeof(MsgHeader)));
-            CU(cudaMemset(s.recv[k][side], 0, sizeof(MsgHeader)));
+        for (int side = 0; side < 2; ++side) {   // (counts only: seq / ack follow the cluster's rounds)
+            CU(cudaMemset(&s.send[k][side]->count, 0, sizeof(uint32_t)));
+            CU(cudaMemset(&s.recv[k][side]->count, 0, sizeof(uint32_t)));
         }
     c->loaded = true;
     return 0;
@@ -874,22 +1064,26 @@ int sph_cluster_rebalance(sph_cluster *c) {
         }
         rc = wait_taken(c, s, kMigrate);
         if (rc) return rc;
-        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(s.send[kMigrate][side], 0, sizeof(MsgHeader), s.core.stream));
+        before_pack(c, s, kMigrate);
+        for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(&s.send[kMigrate][side]->count, 0, sizeof(uint32_t), s.core.stream));
         if (moved) {
             const Params p = launch_params(s, c->cap);
             launch_rekey_emigrate(p, *s.core.d, s.core.stream);
             c->launches += 1;
         }
+        after_pack(c, s, kMigrate);
     }
+    const uint32_t round_m = c->round[kMigrate];
     rc = exchange(c, kMigrate);
     if (rc) return rc;
     for (Slab &s : c->slabs) {
         CU(cudaSetDevice(s.device));
         const Params p = launch_params(s, c->cap);
         // (rebalance = true: append behind n_total and keep the earlier dead entries counted)
-        launch_append_immigrants(p, *s.core.d, msg_or_null(c, s, s.recv[kMigrate][0], 0),
-                                 msg_or_null(c, s, s.recv[kMigrate][1], 1), c->cap_m, s.send[kMigrate][0],
-                                 s.send[kMigrate][1], c->cap, s.dyn, true, s.core.stream);
+        before_unpack(c, s, kMigrate, round_m);
+        launch_append_immigrants(p, *s.core.d, in_msg(c, s, kMigrate, 0), in_msg(c, s, kMigrate, 1), c->cap_m,
+                                 s.send[kMigrate][0], s.send[kMigrate][1], c->cap, s.dyn, true, s.core.stream);
+        after_unpack(c, s, kMigrate, round_m);
         CU(cudaMemcpyAsync(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, s.core.stream));
         c->launches += 2;
     }

@@ -60,10 +60,13 @@ struct Params {
     int nz;         // global cells along z
     float hi_z;     // global box length along z minus h (z wall)
     uint32_t dead_key;  // slab: key given to emigrated particles; sorts behind every live key
-    // -- launch over a subset of the particle CTAs (slab mode: interior CTAs run while the halo is in
-    //    flight, boundary CTAs afterwards); CTA c of the grid works on particle CTA
-    //    c + (c >= cta_gap_at ? cta_gap_len : 0); cta_count = grid size, 0 = all CTAs
-    int cta_gap_at, cta_gap_len, cta_count;
+    // -- launch over a subset of the particle CTAs (slab cluster: the interior CTAs run before the halo
+    //    is waited for, the boundary CTAs after it arrived).  part 0 = every CTA; 1 = interior only
+    //    (a CTA that holds a particle of the lowest / highest owned layer skips); 2 = those boundary CTAs
+    //    only, launched as 2 * part_ctas blocks (low boundary, then high boundary).  The boundary
+    //    ranges come from SlabDyn (n_live, lo_count, hi_count), i.e. they are decided on the device.
+    int part, part_ctas;
+    int cta_count;        // grid size to launch, 0 = one CTA per kBlock particles of n
     const SlabDyn *dyn;   // slab cluster: counts in device memory (n, n_owned are then upper bounds)
     // -- self-checking build (-DSPH_BOUNDS_CHECK; compute-sanitizer is closed on the GPU pool)
     int slot_begin, slot_end;   // sorted slots that hold particles this step (ghosts included)
@@ -88,10 +91,19 @@ enum : uint32_t {
 // Live particles of this step: a host-known launch parameter, or the slab's device-side count.
 __device__ __forceinline__ int live_count(const Params &p) { return p.dyn ? p.dyn->n_live : p.n; }
 
-// Particle CTA this thread block works on (see Params::cta_gap_at).
+// Particle CTA (kBlockParticles consecutive sorted particles) this thread block works on, or -1 if
+// the block has nothing to do in this launch (see Params::part).
+constexpr int kBlockParticles = 128;
 __device__ __forceinline__ int particle_cta(const Params &p) {
     const int c = (int)blockIdx.x;
-    return c + (c >= p.cta_gap_at ? p.cta_gap_len : 0);
+    if (p.part == 0) return c;
+    const int n = p.dyn->n_live;
+    const int lo_end = (p.dyn->lo_count + kBlockParticles - 1) / kBlockParticles;          // CTAs [0, lo_end) touch the lowest layer
+    const int hi_first = max((n - p.dyn->hi_count) / kBlockParticles, lo_end);             // CTAs [hi_first, ...) the highest
+    if (p.part == 1) return (c < lo_end || c >= hi_first) ? -1 : c;
+    if (c < p.part_ctas) return c < lo_end ? c : -1;
+    const int h = hi_first + (c - p.part_ctas);
+    return h * kBlockParticles < n ? h : -1;
 }
 
 // ---- cell coordinates and keys ------------------------------------------------

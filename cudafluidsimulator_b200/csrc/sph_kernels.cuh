@@ -47,12 +47,23 @@ struct DeviceState {
 };
 
 // Header of a message between neighbouring slabs (cluster mode); the payload follows it.
+// count : entries in the payload (the migration message's count is the force kernel's atomic cursor)
+// seq   : written by the SENDER after the payload of exchange round `seq` is complete
+// ack   : written by the RECEIVER (into the sender's memory) once it has consumed round `ack`
+// seq / ack are only used between slabs of different processes, where the receiver reads the
+// sender's buffer directly over NVLink (peer memory); they sit in separate 64-byte blocks.
 struct MsgHeader {
     uint32_t count;
-    uint32_t pad[3];
+    uint32_t pad0[3];
+    uint32_t seq;
+    uint32_t pad1[11];
+    uint32_t ack;
+    uint32_t pad2[15];
 };
+static_assert(sizeof(MsgHeader) == 128, "message payloads start 128-byte aligned");
 
 constexpr int kBlock = 128;      // particles per CTA of the neighbour kernels (ref: simulator.cu:12)
+static_assert(kBlock == kBlockParticles, "particle_cta() assumes the neighbour kernels' CTA size");
 constexpr int kMaskWords = 64;   // mask capacity per particle: 64 words = up to 2048 candidates
 constexpr uint32_t kNoMaskRows = 0xffffffffu;
 constexpr int kMaskRowsPerWarp = 12;  // pool size: average rows per warp (48 B per particle)
@@ -98,5 +109,9 @@ void launch_append_immigrants(const Params &p, const DeviceState &d, const MsgHe
                               const MsgHeader *sent_hi, int capacity, SlabDyn *dyn, bool rebalance,
                               cudaStream_t s);
 void launch_rekey_emigrate(const Params &p, const DeviceState &d, cudaStream_t s);
+// peer-memory hand-shake on up to two message headers (either may be null), one tiny kernel each:
+// wait until seq / ack reaches `round`, or set it (after a system-wide fence)
+enum MsgFlagOp : int { kWaitSeq = 0, kWaitAck = 1, kSetSeq = 2, kSetAck = 3 };
+void launch_msg_flags(int op, MsgHeader *h0, MsgHeader *h1, uint32_t round, cudaStream_t s);
 
 }  // namespace sph
