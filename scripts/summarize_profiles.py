@@ -80,19 +80,8 @@ def full_table(rep, heading):
             lines.append(f"| {short} | " + " | ".join(f"{v:.2f}" for v in vals) + " |")
 
 
-if len(sys.argv) > 4:   # the sparse regime first appended after the developed state below
-    early = Path(sys.argv[4])
-else:
-    early = None
-full_table(rep, "# state after 100 steps (scripts/profile_step.py --pre 100): mean candidates 116, mean neighbours 25.")
-dev = (h2, units, d2, jx, names)
-if early is not None:
-    full_table(early, "# state after 3 steps (--pre 3, the undisturbed lattice: the sparse regime): mean candidates 39, mean neighbours 7."
-               " (Captured before the sort's ballot step was rewritten: its k_onesweep columns are ~7 % slower than the final code.)")
-h2, units, d2, jx, names = dev   # the traffic file below describes the developed state
-(out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
+early = Path(sys.argv[4]) if len(sys.argv) > 4 else None
 
-# per-launch DRAM traffic of every kernel (bench.py reports it as roofline.traffic)
 import json
 
 
@@ -101,13 +90,24 @@ def _bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
 
 
-traffic = {}
-for r, nm in zip(d2, names):
-    rd = _bytes(r[jx["dram__bytes_read.sum"]], units[jx["dram__bytes_read.sum"]])
-    wr = _bytes(r[jx["dram__bytes_write.sum"]], units[jx["dram__bytes_write.sum"]])
-    traffic.setdefault(nm, []).append(rd + wr)
-(out / f"{tag}_traffic.json").write_text(json.dumps(
-    {"source": f"profiles/{tag}_ncu_summary.md: ncu --set full, one step of the 16M grid workload after 100 steps; "
-               "dram__bytes_read.sum + dram__bytes_write.sum per launch",
-     "bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}}, indent=1) + "\n")
+def write_traffic(suffix, what):
+    """per-launch DRAM traffic of every kernel of the capture just tabulated (bench.py reports it as
+    roofline.traffic for the run whose state matches)"""
+    traffic = {}
+    for r, nm in zip(d2, names):
+        rd = _bytes(r[jx["dram__bytes_read.sum"]], units[jx["dram__bytes_read.sum"]])
+        wr = _bytes(r[jx["dram__bytes_write.sum"]], units[jx["dram__bytes_write.sum"]])
+        traffic.setdefault(nm, []).append(rd + wr)
+    (out / f"{tag}_traffic_{suffix}.json").write_text(json.dumps(
+        {"source": f"profiles/{tag}_ncu_summary.md: ncu --set full --clock-control none, one plainly launched step of the "
+                   f"16M grid workload {what}; dram__bytes_read.sum + dram__bytes_write.sum per launch",
+         "bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}}, indent=1) + "\n")
+
+
+full_table(rep, "# state after 100 steps (scripts/profile_step.py --pre 100, the floor pile-up): mean candidates 116, mean neighbours 25.")
+write_traffic("late", "after 100 steps (floor pile-up, mean candidates 116)")
+if early is not None:
+    full_table(early, "# state after 3 steps (--pre 3, the undisturbed lattice: the sparse regime): mean candidates 39, mean neighbours 7.")
+    write_traffic("early", "after 3 steps (undisturbed lattice, mean candidates 39)")
+(out / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
 print("\n".join(lines))
