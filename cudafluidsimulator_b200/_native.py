@@ -16,6 +16,8 @@ LIB_PATH = Path(os.environ.get("SPH_B200_LIB", PKG / "libsph_b200.so"))
 
 SPH_KEY_FLAT = 0
 SPH_KEY_MORTON = 1
+SPH_SORT_COUNT = 1
+SPH_SORT_RADIX = 2
 SPH_STAGE_COUNT = 8
 
 
@@ -47,7 +49,7 @@ class SphOptions(C.Structure):
         ("no_mask_handoff", C.c_int32),
         ("nz_cells", C.c_int32), ("ghost_capacity", C.c_int32), ("emig_capacity", C.c_int32),
         ("pipeline_readback", C.c_int32), ("stage_tiles", C.c_int32),
-        ("density_sum", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("density_sum", C.c_int32), ("sort_algo", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

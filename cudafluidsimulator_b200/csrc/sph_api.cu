@@ -64,6 +64,9 @@ struct sph_sim {
     int sm_count = 148;
     int capacity = 0;
     int passes = 0;
+    bool cell_sort = false;     // counting sort by cell instead of the radix passes (single GPU)
+    bool fuse_count = false;    // ... with the count produced by the previous step's force kernel
+    bool counted = false;       // d.cell_count / d.pairs[1] describe the current state (fused count ran)
     int sorted_buf = 0;
     cudaStream_t stream = nullptr;
     float *host_pos = nullptr;  // pinned, 3*n floats, original order
@@ -135,8 +138,23 @@ void enqueue_build(sph_sim *s) {
         launch_hash(s->p, s->d, s->stream);
         stage_end(s);
         s->keys_valid = true;
+        if (s->counted) {   // counts of a state that was replaced
+            cudaMemsetAsync(s->d.cell_count, 0, ((size_t)s->p.table_size + 1) * sizeof(uint32_t), s->stream);
+            s->counted = false;
+        }
     }
     SortHooks hooks{s, sort_before, sort_after};
+    if (s->cell_sort) {
+        cell_sort_async(s->d.key, s->d.pairs[0], s->d.pairs[1], s->p.n, s->p.table_size + 1u, s->d.cell_count,
+                        s->d.cell_start, s->d.sort_scratch, s->stream, &hooks, s->counted);
+        s->counted = false;
+        s->sorted_buf = 0;
+        s->d.sorted_pairs = s->d.pairs[0];
+        stage_begin(s, kStReorder);
+        launch_reorder_counted(s->p, s->d, 0, s->stream);
+        stage_end(s);
+        return;
+    }
     s->sorted_buf = sort_pairs_async(s->d.key, s->d.pairs[0], s->d.pairs[1], s->p.n, s->passes,
                                      s->d.sort_scratch, s->sm_count, s->stream, &hooks);
     s->d.sorted_pairs = s->d.pairs[s->sorted_buf];
@@ -150,16 +168,19 @@ void enqueue_update(sph_sim *s) {
     launch_density(s->p, s->th, s->d, false, s->stream);
     stage_end(s);
     stage_begin(s, kStForce);
-    launch_force_integrate(s->p, s->th, s->d, s->stream);
+    launch_force_integrate(s->p, s->th, s->d, s->stream, s->fuse_count);
     stage_end(s);
+    s->counted = s->fuse_count;
 }
 
-int graph_launches_per_step(const sph_sim *s) { return 1 /*hist*/ + s->passes + 3; }
+int sort_launches(const sph_sim *s) { return s->cell_sort ? 3 /*scan sums, scan, scatter*/ : s->passes; }
+int hist_launches(const sph_sim *s) { return s->fuse_count ? 0 : 1; }   // histogram / count kernel
+int graph_launches_per_step(const sph_sim *s) { return hist_launches(s) + sort_launches(s) + 3; }
 
 // One timestep on the stream; graph replay when possible.
 int enqueue_step(sph_sim *s) {
     const bool want_graph = s->opt.use_graph != 2 && !s->profiling;
-    if (want_graph && s->keys_valid) {
+    if (want_graph && s->keys_valid && s->counted == s->fuse_count) {
         cudaGraphExec_t &graph_slot = !s->d.out_pos ? s->graph_noout : (s->out_parity ? s->graph_alt : s->graph);
         if (!graph_slot) {
             cudaGraph_t g = nullptr;
@@ -177,8 +198,8 @@ int enqueue_step(sph_sim *s) {
         }
         CU(cudaGraphLaunch(graph_slot, s->stream));
         s->launches += graph_launches_per_step(s);
-        s->stage_launches[kStHist] += 1;
-        s->stage_launches[kStSort] += s->passes;
+        s->stage_launches[kStHist] += hist_launches(s);
+        s->stage_launches[kStSort] += sort_launches(s);
         s->stage_launches[kStReorder] += 1;
         s->stage_launches[kStDensity] += 1;
         s->stage_launches[kStForce] += 1;
@@ -194,7 +215,8 @@ int enqueue_step(sph_sim *s) {
 // One half of the step ("Grid construction" or "SPH update" bucket) as a graph replay: at small N
 // the step is launch-bound (hist + 3 passes + reorder = 6 launches for ~30 us of work).
 int enqueue_half(sph_sim *s, bool build) {
-    const bool want_graph = s->opt.use_graph != 2 && !s->profiling && s->keys_valid;
+    const bool want_graph = s->opt.use_graph != 2 && !s->profiling && s->keys_valid &&
+                            (build ? s->counted == s->fuse_count : true);
     if (!want_graph) {
         if (build) enqueue_build(s); else enqueue_update(s);
         return 0;
@@ -214,9 +236,10 @@ int enqueue_half(sph_sim *s, bool build) {
         memcpy(s->stage_launches, sl0, sizeof(sl0));
     }
     CU(cudaGraphLaunch(slot, s->stream));
+    s->counted = build ? false : s->fuse_count;   // (what enqueue_build / enqueue_update record when launched plainly)
     if (build) {
-        s->launches += 2 + s->passes;
-        s->stage_launches[kStHist] += 1; s->stage_launches[kStSort] += s->passes; s->stage_launches[kStReorder] += 1;
+        s->launches += 1 + hist_launches(s) + sort_launches(s);
+        s->stage_launches[kStHist] += hist_launches(s); s->stage_launches[kStSort] += sort_launches(s); s->stage_launches[kStReorder] += 1;
     } else {
         s->launches += 2;
         s->stage_launches[kStDensity] += 1; s->stage_launches[kStForce] += 1;
@@ -287,7 +310,7 @@ int free_device(sph_sim *s) {
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     s->copy_stream = nullptr;
     s->ev_step = s->ev_copy = nullptr;
-    cudaFree(d.sort_scratch); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.masks.words); cudaFree(d.masks.base); cudaFree(d.masks.cursor); cudaFree(d.pair_xy); cudaFree(d.pair_z);
+    cudaFree(d.sort_scratch); cudaFree(d.cell_count); cudaFree(d.stats); cudaFree(d.counts); cudaFree(d.masks.words); cudaFree(d.masks.base); cudaFree(d.masks.cursor); cudaFree(d.pair_xy); cudaFree(d.pair_z);
     cudaFree(s->p.dbg);
     s->p.dbg = nullptr;
     memset(&d, 0, sizeof(d));
@@ -423,6 +446,13 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
         p.table_size = 1u << (3 * bits);
     }
     s->passes = sort_passes_for(p.table_size);
+    {   // the step's sort: counting sort by cell on a single GPU unless the radix passes are asked for
+        const char *e = getenv("SPH_SORT");
+        const bool radix = s->opt.sort_algo == SPH_SORT_RADIX || (s->opt.sort_algo == 0 && e && !strcmp(e, "radix"));
+        s->cell_sort = !p.slab && !radix;
+        const char *f = getenv("SPH_FUSE_COUNT");
+        s->fuse_count = s->cell_sort && p.key_mode == SPH_KEY_FLAT && !(f && !strcmp(f, "0"));
+    }
     s->th.r2_eps = bisect_sqrt_threshold(kEps, true);
     s->th.r2_h = bisect_sqrt_threshold(st->h, false);
     s->capacity = s->opt.capacity > p.n ? s->opt.capacity : p.n;
@@ -493,7 +523,16 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
             CU(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
         }
     }
-    CU(cudaMalloc(&d.sort_scratch, sort_scratch_words((int)cap) * sizeof(uint32_t)));
+    {
+        size_t words = sort_scratch_words((int)cap);
+        if (s->cell_sort) {
+            words = std::max(words, cell_sort_scratch_words(s->p.table_size + 1u));
+            const size_t entries = (size_t)s->p.table_size + 1 + 3;   // the scan moves whole uint4
+            CU(cudaMalloc(&d.cell_count, entries * sizeof(uint32_t)));
+            CU(cudaMemsetAsync(d.cell_count, 0, entries * sizeof(uint32_t), s->stream));
+        }
+        CU(cudaMalloc(&d.sort_scratch, words * sizeof(uint32_t)));
+    }
     CU(cudaMalloc(&d.stats, 2 * sizeof(double)));
     CU(cudaMalloc(&s->p.dbg, sizeof(uint32_t)));
     CU(cudaMemsetAsync(s->p.dbg, 0, sizeof(uint32_t), s->stream));

@@ -188,4 +188,30 @@ __device__ __forceinline__ void for_each_run(const Params &p, int cx, int cy, in
     }
 }
 
+
+// Counting sort by cell (sph_sort.cu): registers the calling lane's key in count[] and returns the
+// lane's provisional rank inside its cell.  Lanes that are neighbours in the warp and share a key
+// join in one atomic (the array is last step's sorted order: neighbours mostly share a cell).
+// All 32 lanes call it together; `active` = the lane has a particle.
+__device__ __forceinline__ uint32_t cell_rank(uint32_t *__restrict__ count, uint32_t key, bool active) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t k = active ? key : 0xffffffffu;   // never equal to a cell number
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, k, 1);
+    const bool head = lane == 0 || k != prev;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t upto = (2u << lane) - 1u;         // lanes <= mine (lane 31: all)
+    const int start = 31 - __clz(heads & upto);
+    const uint32_t above = heads & ~upto;
+    const int end = above ? __ffs(above) - 1 : 32;
+    uint32_t base = 0;
+    if (head && active) base = atomicAdd(count + k, (uint32_t)(end - start));
+    base = __shfl_sync(0xffffffffu, base, start);
+    return base + (uint32_t)(lane - start);
+}
+// Output of the count fused into the force kernel: next step's counts and tagged pairs.
+struct CellCount {
+    uint32_t *count;    // nullptr: not fused
+    uint64_t *tagged;   // (key << 32 | provisional rank) per particle of the new state
+};
+
 }  // namespace sph

@@ -21,6 +21,7 @@ struct DeviceState {
     float4 *force;               // optional: force of the last step per sorted slot
     float *out_pos;              // xyz packed, ORIGINAL particle order (host readback source)
     uint32_t *sort_scratch;
+    uint32_t *cell_count;   // counting sort by cell: table_size + 1 words, zero between steps
     double *stats;               // 2 doubles
     int32_t *counts;             // optional 2*n scratch for K and C
     const uint64_t *sorted_pairs;  // pairs[sorted buffer] of this step: key of sorted slot i in the high word
@@ -83,9 +84,14 @@ struct Thresholds {
 void launch_hash(const Params &p, const DeviceState &d, cudaStream_t s);
 void launch_reorder(const Params &p, const DeviceState &d, int sorted_buf, int n_sorted, int sm_count,
                     cudaStream_t s);
+// Single-GPU step after cell_sort_async(): pairs grouped by cell, cell_start already built.
+void launch_reorder_counted(const Params &p, const DeviceState &d, int sorted_buf, cudaStream_t s);
 void launch_density(const Params &p, const Thresholds &t, const DeviceState &d, bool counts,
                     cudaStream_t s);
-void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s);
+// count_cells (single GPU, flat keys): also produce next step's per-cell counts (d.cell_count) and
+// tagged pairs (d.pairs[1]) for the counting sort by cell.
+void launch_force_integrate(const Params &p, const Thresholds &t, const DeviceState &d, cudaStream_t s,
+                            bool count_cells = false);
 // positions of the state (cur_pos, id in .w) -> xyz packed in ORIGINAL particle order
 void launch_unpermute(const Params &p, const DeviceState &d, float *out_pos, cudaStream_t s);
 void launch_push(const Params &p, const DeviceState &d, int click_x, int click_y, cudaStream_t s);

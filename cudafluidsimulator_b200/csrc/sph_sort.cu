@@ -13,6 +13,7 @@
 // per pass 8 read + 8 written (first pass reads only the 4-byte key, the index
 // is implicit).
 #include "sph_sort.cuh"
+#include "sph_common.cuh"
 
 // Tunables of the onesweep pass (see profiles/r01_sort_phase_elimination.txt): resident CTAs
 // per SM and status words fetched per look-back step.  The look-back walk covers every
@@ -373,6 +374,189 @@ __global__ void __launch_bounds__(kSortThreads, SORT_CTAS_PER_SM)
     TRACE(5);
 }
 
+
+// ===== counting sort by cell (single-GPU step) ===========================================
+// The keys are cell numbers below table_size, and the step needs the exclusive prefix of the
+// per-cell counts anyway (cell_start).  So instead of three digit passes over the pairs:
+//   k_cell_count    count[key]++ with the old value kept as the particle's provisional rank
+//                   in its cell (warp-aggregated over runs of equal keys: the input is last
+//                   step's sorted order, neighbours in the array mostly share a cell)
+//   k_cell_scan_*   cell_start = exclusive prefix of count (tile and group sums, then one sweep
+//                   that also zeroes count for the next step)
+//   k_cell_scatter  pair (key, index) -> slot cell_start[key] + provisional rank
+// The provisional ranks are in atomic (= arbitrary) order; the reorder kernel that follows
+// replaces them by the rank of the index among the cell's members (k_reorder<COUNTED>), so
+// the final order is (key, index) exactly as the stable radix sort produces it -- the
+// summation order downstream, and with it every result, stays deterministic.
+// Algorithmic bytes per particle: 4 + 8 (count) + 8 + 4 + 8 (scatter) = 32, plus 12 per table
+// entry (scan), against 4 + 16 P - 4 for P radix passes.
+constexpr int kScanThreads = 256;
+constexpr int kScanVecs = 4;                                   // uint4 loads per thread
+constexpr int kScanTile = kScanThreads * kScanVecs * 4;        // 4096 table entries per CTA
+
+__global__ void __launch_bounds__(256)
+    k_cell_count(const uint32_t *__restrict__ keys, int n, uint32_t *__restrict__ count,
+                 uint64_t *__restrict__ tagged) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t key = i < n ? __ldg(keys + i) : 0u;
+    const uint32_t r = cell_rank(count, key, i < n);
+    if (i < n) tagged[i] = ((uint64_t)key << 32) | r;
+}
+
+// Scan, part 1: sum of every tile of 4096 counts, and of every group of `group` tiles.
+__global__ void __launch_bounds__(kScanThreads)
+    k_cell_scan_sums(const uint32_t *__restrict__ count, uint32_t entries, uint32_t *__restrict__ tile_sum,
+                     uint32_t *__restrict__ group_sum, uint32_t group_shift) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t tile_base = tile * (uint32_t)kScanTile;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int v = 0; v < kScanVecs; ++v) {
+        const uint32_t e = tile_base + (uint32_t)((v * kScanThreads + tid) * 4);
+        if (e + 3 < entries) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(count + e));
+            sum += q.x + q.y + q.z + q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (e + j < entries) sum += __ldg(count + e + j);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) t += s_warp[w];
+        tile_sum[tile] = t;
+        if (t) atomicAdd(group_sum + (tile >> group_shift), t);
+    }
+}
+
+// Scan, part 2: cell_start = exclusive prefix of count; count is cleared for the next step.  The
+// tile's offset = the groups before its group + the tiles before it inside the group (at most
+// 2 * sqrt(tiles) words, read by every CTA: no chain between CTAs -- a decoupled look-back was
+// measured first and spent its time walking the ~1000 tiles in flight).
+__global__ void __launch_bounds__(kScanThreads)
+    k_cell_scan_apply(uint32_t *__restrict__ count, uint32_t *__restrict__ cell_start, uint32_t entries,
+                      const uint32_t *__restrict__ tile_sum, const uint32_t *__restrict__ group_sum,
+                      uint32_t group_shift) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_off[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t tile_base = tile * (uint32_t)kScanTile;
+
+    // offset of the tile
+    uint32_t off = 0;
+    {
+        const uint32_t g = tile >> group_shift;
+        for (uint32_t k = tid; k < g; k += kScanThreads) off += __ldg(group_sum + k);
+        for (uint32_t k = (g << group_shift) + tid; k < tile; k += kScanThreads) off += __ldg(tile_sum + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+        if (lane == 0) s_off[warp] = off;
+    }
+
+    // warp-striped uint4 loads: vector v of warp w covers entries tile_base + ((w*4+v)*32 + lane)*4 ..+3
+    uint32_t c[kScanVecs][4];
+    uint32_t vsum[kScanVecs];
+#pragma unroll
+    for (int v = 0; v < kScanVecs; ++v) {
+        const uint32_t e = tile_base + (uint32_t)(((warp * kScanVecs + v) * 32 + lane) * 4);
+        if (e + 3 < entries) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(count + e);
+            c[v][0] = q.x; c[v][1] = q.y; c[v][2] = q.z; c[v][3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c[v][j] = 0;
+                if (e + j < entries) c[v][j] = count[e + j];
+            }
+        }
+        vsum[v] = c[v][0] + c[v][1] + c[v][2] + c[v][3];
+    }
+    // exclusive prefix of every vector inside its warp
+    uint32_t vexcl[kScanVecs];
+    uint32_t run = 0;
+#pragma unroll
+    for (int v = 0; v < kScanVecs; ++v) {
+        uint32_t incl = vsum[v];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        vexcl[v] = run + incl - vsum[v];
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_warp[warp] = run;
+    __syncthreads();
+    uint32_t prefix = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        prefix += s_off[w];
+        if (w < warp) prefix += s_warp[w];
+    }
+#pragma unroll
+    for (int v = 0; v < kScanVecs; ++v) {
+        const uint32_t e = tile_base + (uint32_t)(((warp * kScanVecs + v) * 32 + lane) * 4);
+        uint4 o;
+        o.x = prefix + vexcl[v];
+        o.y = o.x + c[v][0];
+        o.z = o.y + c[v][1];
+        o.w = o.z + c[v][2];
+        if (e + 3 < entries) {
+            *reinterpret_cast<uint4 *>(cell_start + e) = o;
+        } else {
+            if (e < entries) cell_start[e] = o.x;
+            if (e + 1 < entries) cell_start[e + 1] = o.y;
+            if (e + 2 < entries) cell_start[e + 2] = o.z;
+        }
+    }
+    // count is cleared only now: a store to count between the loads above made every later load
+    // wait for it (the compiler cannot tell the addresses apart) -- 156 us instead of 19 us at 16 M cells
+#pragma unroll
+    for (int v = 0; v < kScanVecs; ++v) {
+        const uint32_t e = tile_base + (uint32_t)(((warp * kScanVecs + v) * 32 + lane) * 4);
+        if (e + 3 < entries) {
+            *reinterpret_cast<uint4 *>(count + e) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (e + j < entries) count[e + j] = 0;
+        }
+    }
+}
+
+// Four particles per thread, all loads of a stage issued together: the kernel is a chain of two
+// dependent loads and a store per particle, and one chain per thread was latency-bound (75-98 us at
+// 16 M against ~45 us of traffic).
+constexpr int kScatterItems = 4;
+__global__ void __launch_bounds__(256)
+    k_cell_scatter(const uint64_t *__restrict__ tagged, int n, const uint32_t *__restrict__ cell_start,
+                   uint64_t *__restrict__ pairs) {
+    const int i0 = blockIdx.x * (256 * kScatterItems) + threadIdx.x;
+    uint64_t t[kScatterItems];
+    uint32_t c0[kScatterItems];
+#pragma unroll
+    for (int k = 0; k < kScatterItems; ++k) {
+        const int i = i0 + k * 256;
+        t[k] = i < n ? __ldg(tagged + i) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kScatterItems; ++k) c0[k] = __ldg(cell_start + (uint32_t)(t[k] >> 32));
+#pragma unroll
+    for (int k = 0; k < kScatterItems; ++k) {
+        const int i = i0 + k * 256;
+        if (i < n) pairs[c0[k] + (uint32_t)t[k]] = (t[k] & 0xffffffff00000000ull) | (uint32_t)i;
+    }
+}
+
 }  // namespace
 
 int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
@@ -423,6 +607,49 @@ int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, i
         if (hooks) hooks->after(hooks->ctx, kSortStagePass);
     }
     return out;
+}
+
+
+namespace {
+uint32_t scan_tiles(uint32_t table_entries) { return (table_entries + kScanTile - 1) / kScanTile; }
+uint32_t scan_group_shift(uint32_t tiles) {   // groups of 2^shift tiles, about sqrt(tiles) of them
+    uint32_t shift = 0;
+    while ((1ull << (2 * shift)) < tiles) ++shift;
+    return shift;
+}
+}  // namespace
+
+size_t cell_sort_scratch_words(uint32_t table_entries) {
+    const uint32_t tiles = scan_tiles(table_entries);
+    return (size_t)tiles + (tiles >> scan_group_shift(tiles)) + 1;   // [group sums][tile sums]
+}
+
+void cell_sort_async(const uint32_t *keys, uint64_t *pairs_sorted, uint64_t *pairs_tmp, int n,
+                     uint32_t table_entries, uint32_t *count, uint32_t *cell_start, uint32_t *scratch,
+                     cudaStream_t stream, SortHooks *hooks, bool counted) {
+    const uint32_t tiles = scan_tiles(table_entries);
+    const uint32_t shift = scan_group_shift(tiles);
+    const uint32_t groups = (tiles >> shift) + 1;
+    uint32_t *group_sum = scratch, *tile_sum = scratch + groups;
+    cudaMemsetAsync(group_sum, 0, groups * sizeof(uint32_t), stream);
+    const int blocks = (n + 255) / 256;
+    if (!counted) {   // (otherwise the force kernel of the previous step counted: CellCount)
+        if (hooks) hooks->before(hooks->ctx, kSortStageHistogram);
+        if (n > 0) k_cell_count<<<blocks, 256, 0, stream>>>(keys, n, count, pairs_tmp);
+        if (hooks) hooks->after(hooks->ctx, kSortStageHistogram);
+    }
+    if (hooks) hooks->before(hooks->ctx, kSortStagePass);
+    k_cell_scan_sums<<<tiles, kScanThreads, 0, stream>>>(count, table_entries, tile_sum, group_sum, shift);
+    if (hooks) hooks->after(hooks->ctx, kSortStagePass);
+    if (hooks) hooks->before(hooks->ctx, kSortStagePass);
+    k_cell_scan_apply<<<tiles, kScanThreads, 0, stream>>>(count, cell_start, table_entries, tile_sum,
+                                                          group_sum, shift);
+    if (hooks) hooks->after(hooks->ctx, kSortStagePass);
+    if (hooks) hooks->before(hooks->ctx, kSortStagePass);
+    if (n > 0)
+        k_cell_scatter<<<(n + 256 * kScatterItems - 1) / (256 * kScatterItems), 256, 0, stream>>>(
+            pairs_tmp, n, cell_start, pairs_sorted);
+    if (hooks) hooks->after(hooks->ctx, kSortStagePass);
 }
 
 }  // namespace sph

@@ -87,7 +87,8 @@ class Simulator:
 
     def __init__(self, settings: Settings, *, key_mode: int = SPH_KEY_FLAT, device: int = 0,
                  record_force: bool = False, use_graph: bool = True, mask_handoff: bool = True,
-                 pipeline_readback: bool = False, stage_tiles: bool = False, density_sum: int = 0):
+                 pipeline_readback: bool = False, stage_tiles: bool = False, density_sum: int = 0,
+                 sort_algo: int = 0):
         self.settings = settings
         self._lib = N.load()
         opt = N.SphOptions()
@@ -99,6 +100,7 @@ class Simulator:
         opt.pipeline_readback = 1 if pipeline_readback else 0
         opt.stage_tiles = 1 if stage_tiles else 0
         opt.density_sum = int(density_sum)
+        opt.sort_algo = int(sort_algo)   # 0 default, 1 counting sort by cell, 2 radix passes
         h = C.c_void_p()
         cs = settings.to_c()
         N.check(self._lib.sph_create_ex(C.byref(cs), C.byref(opt), C.byref(h)))

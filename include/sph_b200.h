@@ -70,6 +70,9 @@ enum {
                              ref: simulator.cu:60-73)                           */
 };
 
+#define SPH_SORT_COUNT 1
+#define SPH_SORT_RADIX 2
+
 /* Extra, additive knobs; zero-initialise for reference behaviour. */
 typedef struct SphOptions {
     int32_t device;       /* CUDA device ordinal (default 0)                     */
@@ -103,7 +106,13 @@ typedef struct SphOptions {
                              serial restatement of simulator.cu:163-185), 2 = factored,
                              rho = (m dk) * sum (h^2 - r^2)^3 with two interleaved partial sums (a few
                              ulp away; the reference's own order is its CAS race order)           */
-    int32_t reserved[2];
+    int32_t sort_algo;    /* how a single GPU sorts particles by cell every step: 0 = library default
+                             (SPH_SORT_COUNT unless the environment says SPH_SORT=radix),
+                             SPH_SORT_COUNT = counting sort by cell (per-cell counts, one scan of the
+                             table, scatter; members of a cell ranked by index), SPH_SORT_RADIX =
+                             8-bit onesweep radix passes.  Both give the same order: (key, index).
+                             Slabs of a cluster always use the radix passes.                     */
+    int32_t reserved[1];
 } SphOptions;
 
 /* --- life cycle (ref: Simulator ctor/dtor/setup, simulator.cu:370-460) ------ */
