@@ -519,7 +519,8 @@ def run_ours(args, wl, rank, local_rank, world):
     K, C = sim.get_neighbor_counts()
     meanK, meanC = float(K.mean()), float(C.mean())
     table_size = sim.table_size
-    sort_passes = (max(1, int(table_size - 1).bit_length()) + 7) // 8
+    sort_info = sim.sort_info()   # the library says how it sorts: counting sort by cell, or radix passes
+    sort_passes = sort_info["radix_passes"]
     prof_steps = max(3, min(10, args.steps))
     sim.profile_enable(True)
     sim.profile_read(reset=True)
@@ -567,11 +568,25 @@ def run_ours(args, wl, rank, local_rank, world):
     hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
     clk = clocks.summary()
     f_den, f_force, f_int = flops_per_particle(meanC, meanK)
-    passes = sort_passes          # 8-bit onesweep passes the library runs for this key range
+    passes = sort_passes          # 8-bit onesweep passes a radix sort runs for this key range
+    cells_per_particle = table_size / n
+    if sort_info["algo"] == "count":
+        # counting sort by cell: table scan (sums: R 4; apply: R 4 + W 4 cell_start + W 4 cleared count, per
+        # cell) + scatter (R 8 tagged + R 4 cell_start + W 8 pair); the count itself is part of the force
+        # kernel (+ 8 B tagged pair per particle there) unless it runs as the "histogram" stage (R 4 + W 8)
+        sort_bytes = 16 * cells_per_particle + 20
+        hist_bytes = 12
+        reorder_bytes = 8 + 8 + 32 + 32 + 12          # pair, cell range, gather, sorted copy, pair-interleaved copy
+        force_extra = 8 if sort_info["count_fused"] else 0
+    else:
+        sort_bytes = 4 + 8 + 16 * (passes - 1)
+        hist_bytes = 4
+        reorder_bytes = 8 + 32 + 32 + 12 + 4 * cells_per_particle
+        force_extra = 0
     bytes_stage = {  # algorithmic bytes per particle
-        "hash": 20, "histogram": 4, "sort_passes": 4 + 8 + 16 * (passes - 1),
-        "reorder_cellstart": 8 + 32 + 32 + 12 + 4 * (wl["numCellsPerDim"] ** 3) / n,
-        "density": 16 + 12 + 8, "force_integrate": 16 + 16 + 8 + 4 + 8 + 16 + 16 + 4 + 12,
+        "hash": 20, "histogram": hist_bytes, "sort_passes": sort_bytes,
+        "reorder_cellstart": reorder_bytes,
+        "density": 16 + 12 + 8, "force_integrate": 16 + 16 + 8 + 4 + 8 + 16 + 16 + 4 + 12 + force_extra,
     }
     ncu_kernel = {"density": "k_density_flat", "force_integrate": "k_force_integrate_flat",
                   "reorder_cellstart": "k_reorder", "sort_passes": "k_onesweep<0>", "histogram": "k_histogram"}
@@ -631,7 +646,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(args.workload, wl),
-        "run": {"key": args.key, "parallelism": "single GPU", "sort_passes": sort_passes,
+        "run": {"key": args.key, "parallelism": "single GPU", "sort": sort_info,
                 "state": f"steps {args.warmup + 1}..{args.warmup + args.steps} from the initial condition",
                 "density_sum": "factored (library default)",
                 "l2": "each step consumes the previous step's output (no repeated input); "

@@ -121,6 +121,7 @@ SYMBOLS = {
     "sph_stage_name": (C.c_char_p, [C.c_int]),
     "sph_launch_count": (C.c_int64, [_P]),
     "sph_num_particles": (C.c_int, [_P]),
+    "sph_sort_info": (C.c_int, [_P, _I, _I, _I, _I]),
     "sph_last_error": (C.c_char_p, []),
     "sph_abi_version": (C.c_int, []),
 }

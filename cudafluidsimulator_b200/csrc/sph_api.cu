@@ -449,9 +449,9 @@ int sph_create_ex(const SphSettings *st, const SphOptions *options, sph_sim **ou
     {   // the step's sort: counting sort by cell on a single GPU unless the radix passes are asked for
         const char *e = getenv("SPH_SORT");
         const bool radix = s->opt.sort_algo == SPH_SORT_RADIX || (s->opt.sort_algo == 0 && e && !strcmp(e, "radix"));
-        s->cell_sort = !p.slab && !radix;
+        s->cell_sort = !radix;
         const char *f = getenv("SPH_FUSE_COUNT");
-        s->fuse_count = s->cell_sort && p.key_mode == SPH_KEY_FLAT && !(f && !strcmp(f, "0"));
+        s->fuse_count = s->cell_sort && !p.slab && p.key_mode == SPH_KEY_FLAT && !(f && !strcmp(f, "0"));
     }
     s->th.r2_eps = bisect_sqrt_threshold(kEps, true);
     s->th.r2_h = bisect_sqrt_threshold(st->h, false);
@@ -526,8 +526,8 @@ static int setup_device(sph_sim *s, int n, const std::vector<float> &pos) {
     {
         size_t words = sort_scratch_words((int)cap);
         if (s->cell_sort) {
-            words = std::max(words, cell_sort_scratch_words(s->p.table_size + 1u));
-            const size_t entries = (size_t)s->p.table_size + 1 + 3;   // the scan moves whole uint4
+            words = std::max(words, cell_sort_scratch_words(s->table_capacity + 1u));
+            const size_t entries = (size_t)s->table_capacity + 1 + 3;   // the scan moves whole uint4
             CU(cudaMalloc(&d.cell_count, entries * sizeof(uint32_t)));
             CU(cudaMemsetAsync(d.cell_count, 0, entries * sizeof(uint32_t), s->stream));
         }
@@ -1005,6 +1005,7 @@ int sph_internal_core(sph_sim *s, sph::SlabCore *out) {
     out->sorted_buf = &s->sorted_buf;
     out->device = s->opt.device;
     out->table_capacity = s->table_capacity;
+    out->cell_sort = s->cell_sort;
     return 0;
 }
 
@@ -1046,5 +1047,13 @@ int sph_profile_read(sph_sim *s, double ms[SPH_STAGE_COUNT], int64_t launches[SP
 
 int64_t sph_launch_count(sph_sim *s) { return s ? s->launches : 0; }
 int sph_num_particles(sph_sim *s) { return s ? s->p.n : 0; }
+int sph_sort_info(sph_sim *s, int32_t *algo, int32_t *kernels, int32_t *count_fused, int32_t *radix_passes) {
+    if (!s) return fail(SPH_E_INVALID, "null simulator");
+    if (algo) *algo = s->cell_sort ? SPH_SORT_COUNT : SPH_SORT_RADIX;
+    if (kernels) *kernels = hist_launches(s) + sort_launches(s);
+    if (count_fused) *count_fused = s->fuse_count ? 1 : 0;
+    if (radix_passes) *radix_passes = s->passes;
+    return 0;
+}
 
 }  // extern "C"

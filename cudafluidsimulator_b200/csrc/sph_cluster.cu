@@ -141,6 +141,8 @@ struct Slab {
     double *stats_dev = nullptr;   // 2 doubles
     int *info_dev = nullptr;       // 3 x 8 ints: rebalancing numbers of this slab / from below / from above
     bool hashed = false;
+    bool counted = false;       // d.cell_count / d.pairs[1] hold the next step's counts (fused into force + append)
+    bool count_dirty = false;   // ... or counts that no longer describe the particles: clear before counting
     // SPH_CLUSTER_TRACE=1: CUDA events at the phase boundaries of every step
     std::vector<cudaEvent_t> trace_ev;
     size_t trace_used = 0;
@@ -162,6 +164,7 @@ struct sph_cluster {
     int steps_since_rebalance = 0;
     bool loaded = false;
     bool trace = false;                 // SPH_CLUSTER_TRACE
+    bool fuse_count = false;            // counting sort by cell with the count fused into force + append (SPH_FUSE_COUNT=0: off)
     bool peer_mem = false;              // messages between processes are read in place over NVLink
     uint32_t round[kMsgKinds] = {1, 1, 1};   // exchange rounds so far + 1, per message kind (same on every process)
 };
@@ -353,10 +356,26 @@ int enqueue_step(sph_cluster *c) {
             c->launches += 1;
         }
         mark(c, s);
-        *s.core.sorted_buf = sort_pairs_async(d.key, d.pairs[0], d.pairs[1], cap, *s.core.passes, d.sort_scratch,
-                                              s.core.sm_count, st, nullptr, &s.dyn->n_total);
-        d.sorted_pairs = d.pairs[*s.core.sorted_buf];
-        launch_reorder(p, d, *s.core.sorted_buf, cap, s.core.sm_count, st);
+        if (s.core.cell_sort) {
+            // counting sort by cell over the slab's own table; dead entries (key = the table's last cell)
+            // land behind the live ones as they do after the radix passes
+            if (s.count_dirty) {
+                CU(cudaMemsetAsync(d.cell_count, 0, ((size_t)s.core.table_capacity + 1) * sizeof(uint32_t), st));
+                s.count_dirty = false;
+            }
+            cell_sort_async(d.key, d.pairs[0], d.pairs[1], cap, p.table_size + 1u, d.cell_count, d.cell_start,
+                            d.sort_scratch, st, nullptr, s.counted, &s.dyn->n_total, (uint32_t)p.slot0);
+            *s.core.sorted_buf = 0;
+            d.sorted_pairs = d.pairs[0];
+            launch_reorder_counted(p, d, 0, st);
+            c->launches += (s.counted ? 4 : 5) - (1 + *s.core.passes + 1);   // (the tally below counts the radix launches)
+            s.counted = false;
+        } else {
+            *s.core.sorted_buf = sort_pairs_async(d.key, d.pairs[0], d.pairs[1], cap, *s.core.passes, d.sort_scratch,
+                                                  s.core.sm_count, st, nullptr, &s.dyn->n_total);
+            d.sorted_pairs = d.pairs[*s.core.sorted_buf];
+            launch_reorder(p, d, *s.core.sorted_buf, cap, s.core.sm_count, st);
+        }
         mark(c, s);
         int rc = wait_taken(c, s, kHaloA);
         if (rc) return rc;
@@ -395,7 +414,7 @@ int enqueue_step(sph_cluster *c) {
         if (rc) return rc;
         before_pack(c, s, kMigrate);
         for (int side = 0; side < 2; ++side) CU(cudaMemsetAsync(&s.send[kMigrate][side]->count, 0, sizeof(uint32_t), st));
-        launch_force_integrate(part_params(c, s, 1), *s.core.th, d, st);
+        launch_force_integrate(part_params(c, s, 1), *s.core.th, d, st, c->fuse_count);
         mark(c, s);
         c->launches += 6;
     }
@@ -412,7 +431,7 @@ int enqueue_step(sph_cluster *c) {
         launch_ghost_pa(p, d, in_msg(c, s, kHaloB, 0), in_msg(c, s, kHaloB, 1), c->cap_g, st);
         after_unpack(c, s, kHaloB, round_b);
         mark(c, s);
-        launch_force_integrate(part_params(c, s, 2), *s.core.th, d, st);
+        launch_force_integrate(part_params(c, s, 2), *s.core.th, d, st, c->fuse_count);
         after_pack(c, s, kMigrate);
         mark(c, s);
         c->launches += 2;
@@ -426,7 +445,9 @@ int enqueue_step(sph_cluster *c) {
         const Params p = launch_params(s, cap);
         before_unpack(c, s, kMigrate, round_m);
         launch_append_immigrants(p, *s.core.d, in_msg(c, s, kMigrate, 0), in_msg(c, s, kMigrate, 1), c->cap_m,
-                                 s.send[kMigrate][0], s.send[kMigrate][1], cap, s.dyn, false, s.core.stream);
+                                 s.send[kMigrate][0], s.send[kMigrate][1], cap, s.dyn, false, s.core.stream,
+                                 c->fuse_count);
+        s.counted = c->fuse_count;
         after_unpack(c, s, kMigrate, round_m);
         mark(c, s);
         CU(cudaMemcpyAsync(s.dyn_host, s.dyn, sizeof(SlabDyn), cudaMemcpyDeviceToHost, s.core.stream));
@@ -586,6 +607,10 @@ int sph_cluster_create(const SphSettings *st, const SphClusterOptions *o, sph_cl
     // kernels read them in place.  The handles travel over the NCCL communicator.
     const char *tr = getenv("SPH_CLUSTER_TRACE");
     c->trace = tr && atoi(tr) != 0;
+    {
+        const char *f = getenv("SPH_FUSE_COUNT");
+        c->fuse_count = !c->slabs.empty() && c->slabs[0].core.cell_sort && !(f && !strcmp(f, "0"));
+    }
     const char *force_nccl = getenv("SPH_CLUSTER_NCCL_DATA");
     c->peer_mem = need_nccl && !(force_nccl && atoi(force_nccl) != 0);
     for (size_t i = 0; i < c->slabs.size() && rc == 0 && c->peer_mem; ++i) {
@@ -734,6 +759,7 @@ int sph_cluster_load(sph_cluster *c, int li, int n, const float *pos, const floa
     *s.dyn_host = h;
     s.known_total = n;
     s.hashed = false;
+    if (s.counted) { s.counted = false; s.count_dirty = true; }
     for (int k = 0; k < kMsgKinds; ++k)
         for (int side = 0; side < 2; ++side) {   // (counts only: seq / ack follow the cluster's rounds)
             CU(cudaMemset(&s.send[k][side]->count, 0, sizeof(uint32_t)));
@@ -1061,6 +1087,10 @@ int sph_cluster_rebalance(sph_cluster *c) {
             c->zlo[s.rank] = new_lo[i];
             c->zhi[s.rank] = new_hi[i];
             s.rebalances += 1;
+        }
+        if (s.counted) {   // keys change / particles arrive outside a step: the fused counts are void
+            s.counted = false;
+            s.count_dirty = true;
         }
         rc = wait_taken(c, s, kMigrate);
         if (rc) return rc;

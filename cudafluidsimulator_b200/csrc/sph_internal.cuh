@@ -21,6 +21,7 @@ struct SlabCore {
     int *sorted_buf;
     int device;
     uint32_t table_capacity;
+    bool cell_sort;   // counting sort by cell (d->cell_count allocated) instead of the radix passes
 };
 
 }  // namespace sph

@@ -113,7 +113,7 @@ void launch_ghost_pa(const Params &p, const DeviceState &d, const MsgHeader *msg
 void launch_append_immigrants(const Params &p, const DeviceState &d, const MsgHeader *from_lo,
                               const MsgHeader *from_hi, int cap_m, const MsgHeader *sent_lo,
                               const MsgHeader *sent_hi, int capacity, SlabDyn *dyn, bool rebalance,
-                              cudaStream_t s);
+                              cudaStream_t s, bool count_cells = false);
 void launch_rekey_emigrate(const Params &p, const DeviceState &d, cudaStream_t s);
 // peer-memory hand-shake on up to two message headers (either may be null), one tiny kernel each:
 // wait until seq / ack reaches `round`, or set it (after a system-wide fence)

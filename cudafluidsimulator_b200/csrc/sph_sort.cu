@@ -395,8 +395,10 @@ constexpr int kScanVecs = 4;                                   // uint4 loads pe
 constexpr int kScanTile = kScanThreads * kScanVecs * 4;        // 4096 table entries per CTA
 
 __global__ void __launch_bounds__(256)
-    k_cell_count(const uint32_t *__restrict__ keys, int n, uint32_t *__restrict__ count,
-                 uint64_t *__restrict__ tagged) {
+    k_cell_count(const uint32_t *__restrict__ keys, int n, const int *__restrict__ n_dev,
+                 uint32_t *__restrict__ count, uint64_t *__restrict__ tagged) {
+    if (n_dev) n = *n_dev;   // slab cluster: the count lives on the device, the grid covers the capacity
+    if ((int)(blockIdx.x * 256) >= n) return;
     const int i = blockIdx.x * 256 + threadIdx.x;
     const uint32_t key = i < n ? __ldg(keys + i) : 0u;
     const uint32_t r = cell_rank(count, key, i < n);
@@ -444,15 +446,15 @@ __global__ void __launch_bounds__(kScanThreads)
 __global__ void __launch_bounds__(kScanThreads)
     k_cell_scan_apply(uint32_t *__restrict__ count, uint32_t *__restrict__ cell_start, uint32_t entries,
                       const uint32_t *__restrict__ tile_sum, const uint32_t *__restrict__ group_sum,
-                      uint32_t group_shift) {
+                      uint32_t group_shift, uint32_t base) {
     __shared__ uint32_t s_warp[kScanThreads / 32];
     __shared__ uint32_t s_off[kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)kScanTile;
 
-    // offset of the tile
-    uint32_t off = 0;
+    // offset of the tile (+ base: the slot of the first sorted particle, slot0 of a slab)
+    uint32_t off = tid == 0 ? base : 0u;
     {
         const uint32_t g = tile >> group_shift;
         for (uint32_t k = tid; k < g; k += kScanThreads) off += __ldg(group_sum + k);
@@ -538,8 +540,10 @@ __global__ void __launch_bounds__(kScanThreads)
 // 16 M against ~45 us of traffic).
 constexpr int kScatterItems = 4;
 __global__ void __launch_bounds__(256)
-    k_cell_scatter(const uint64_t *__restrict__ tagged, int n, const uint32_t *__restrict__ cell_start,
-                   uint64_t *__restrict__ pairs) {
+    k_cell_scatter(const uint64_t *__restrict__ tagged, int n, const int *__restrict__ n_dev,
+                   const uint32_t *__restrict__ cell_start, uint32_t base, uint64_t *__restrict__ pairs) {
+    if (n_dev) n = *n_dev;
+    if ((int)(blockIdx.x * (256 * kScatterItems)) >= n) return;
     const int i0 = blockIdx.x * (256 * kScatterItems) + threadIdx.x;
     uint64_t t[kScatterItems];
     uint32_t c0[kScatterItems];
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < kScatterItems; ++k) {
         const int i = i0 + k * 256;
-        if (i < n) pairs[c0[k] + (uint32_t)t[k]] = (t[k] & 0xffffffff00000000ull) | (uint32_t)i;
+        if (i < n) pairs[c0[k] - base + (uint32_t)t[k]] = (t[k] & 0xffffffff00000000ull) | (uint32_t)i;
     }
 }
 
@@ -626,7 +630,7 @@ size_t cell_sort_scratch_words(uint32_t table_entries) {
 
 void cell_sort_async(const uint32_t *keys, uint64_t *pairs_sorted, uint64_t *pairs_tmp, int n,
                      uint32_t table_entries, uint32_t *count, uint32_t *cell_start, uint32_t *scratch,
-                     cudaStream_t stream, SortHooks *hooks, bool counted) {
+                     cudaStream_t stream, SortHooks *hooks, bool counted, const int *n_dev, uint32_t base) {
     const uint32_t tiles = scan_tiles(table_entries);
     const uint32_t shift = scan_group_shift(tiles);
     const uint32_t groups = (tiles >> shift) + 1;
@@ -635,7 +639,7 @@ void cell_sort_async(const uint32_t *keys, uint64_t *pairs_sorted, uint64_t *pai
     const int blocks = (n + 255) / 256;
     if (!counted) {   // (otherwise the force kernel of the previous step counted: CellCount)
         if (hooks) hooks->before(hooks->ctx, kSortStageHistogram);
-        if (n > 0) k_cell_count<<<blocks, 256, 0, stream>>>(keys, n, count, pairs_tmp);
+        if (n > 0) k_cell_count<<<blocks, 256, 0, stream>>>(keys, n, n_dev, count, pairs_tmp);
         if (hooks) hooks->after(hooks->ctx, kSortStageHistogram);
     }
     if (hooks) hooks->before(hooks->ctx, kSortStagePass);
@@ -643,12 +647,12 @@ void cell_sort_async(const uint32_t *keys, uint64_t *pairs_sorted, uint64_t *pai
     if (hooks) hooks->after(hooks->ctx, kSortStagePass);
     if (hooks) hooks->before(hooks->ctx, kSortStagePass);
     k_cell_scan_apply<<<tiles, kScanThreads, 0, stream>>>(count, cell_start, table_entries, tile_sum,
-                                                          group_sum, shift);
+                                                          group_sum, shift, base);
     if (hooks) hooks->after(hooks->ctx, kSortStagePass);
     if (hooks) hooks->before(hooks->ctx, kSortStagePass);
     if (n > 0)
         k_cell_scatter<<<(n + 256 * kScatterItems - 1) / (256 * kScatterItems), 256, 0, stream>>>(
-            pairs_tmp, n, cell_start, pairs_sorted);
+            pairs_tmp, n, n_dev, cell_start, base, pairs_sorted);
     if (hooks) hooks->after(hooks->ctx, kSortStagePass);
 }
 

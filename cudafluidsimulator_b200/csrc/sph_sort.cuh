@@ -41,10 +41,12 @@ int sort_pairs_async(const uint32_t *keys, uint64_t *pairs0, uint64_t *pairs1, i
 // pairs_sorted = the (key, index) pairs grouped by key, members of one cell in arbitrary order --
 // the reorder kernel ranks them by index.  `count` (table_entries words) must be zero on entry and
 // is zero again on exit.  counted: count[] and pairs_tmp (key << 32 | provisional rank) were already
-// produced (by the force kernel of the previous step), skip the count kernel.  `scratch`: cell_sort_scratch_words(table_entries) words.
+// produced (by the force kernel of the previous step), skip the count kernel.  n_dev: as for
+// sort_pairs_async.  base: added to every cell_start entry (slot of the first sorted particle).  `scratch`: cell_sort_scratch_words(table_entries) words.
 size_t cell_sort_scratch_words(uint32_t table_entries);
 void cell_sort_async(const uint32_t *keys, uint64_t *pairs_sorted, uint64_t *pairs_tmp, int n,
                      uint32_t table_entries, uint32_t *count, uint32_t *cell_start, uint32_t *scratch,
-                     cudaStream_t stream, SortHooks *hooks, bool counted);
+                     cudaStream_t stream, SortHooks *hooks, bool counted, const int *n_dev = nullptr,
+                     uint32_t base = 0);
 
 }  // namespace sph

@@ -222,6 +222,13 @@ class Simulator:
     def launch_count(self) -> int:
         return int(self._lib.sph_launch_count(self._h))
 
+    def sort_info(self) -> dict:
+        """{"algo": "count" | "radix", "kernels": sort kernels per step, "count_fused", "radix_passes"}"""
+        v = [C.c_int32() for _ in range(4)]
+        N.check(self._lib.sph_sort_info(self._h, *[C.byref(x) for x in v]))
+        return {"algo": "count" if v[0].value == N.SPH_SORT_COUNT else "radix", "kernels": v[1].value,
+                "count_fused": bool(v[2].value), "radix_passes": v[3].value}
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.sph_destroy(self._h)

@@ -277,6 +277,11 @@ const char *sph_stage_name(int stage);
 /* total kernel launches issued by this simulator so far */
 int64_t sph_launch_count(sph_sim *sim);
 int sph_num_particles(sph_sim *sim);
+/* How this simulator sorts particles by cell: *algo = SPH_SORT_COUNT or SPH_SORT_RADIX, *kernels =
+ * sort kernels launched per step (radix: histogram + passes; count: table scan x2 + scatter, the
+ * count itself being fused into the force kernel when *count_fused), *radix_passes = 8-bit passes
+ * the radix sort needs for this key range. */
+int sph_sort_info(sph_sim *sim, int32_t *algo, int32_t *kernels, int32_t *count_fused, int32_t *radix_passes);
 
 const char *sph_last_error(void);
 int sph_abi_version(void);

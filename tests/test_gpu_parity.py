@@ -30,9 +30,9 @@ RTOL_F = 1e-5
 RTOL_RHO = 2e-6   # density / pressure when the sum is not formed in the oracle's order
 
 
-def make(n, key_mode=sph.SPH_KEY_FLAT, density_sum=0, **kw):
+def make(n, key_mode=sph.SPH_KEY_FLAT, density_sum=0, sort_algo=0, **kw):
     s = sph.Settings(numParticles=n, **kw)
-    sim = sph.Simulator(s, key_mode=key_mode, record_force=True, density_sum=density_sum)
+    sim = sph.Simulator(s, key_mode=key_mode, record_force=True, density_sum=density_sum, sort_algo=sort_algo)
     sim.setup()
     return sim
 
@@ -139,12 +139,19 @@ def test_setup_random_init_matches_reference_rand():
     sim.close()
 
 
+SORTS = [sph.SPH_SORT_COUNT, sph.SPH_SORT_RADIX]
+
+
+@pytest.mark.parametrize("algo", SORTS, ids=["count", "radix"])
 @pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
-def test_sort_is_stable_across_steps(mode):
+def test_sort_is_stable_across_steps(mode, algo):
     """After step k the storage order is step k's sorted order; step k+1 must be a
-    STABLE sort of that order by the new keys (ties keep the previous order)."""
+    STABLE sort of that order by the new keys (ties keep the previous order) -- by the radix
+    passes, and by the counting sort by cell (whose members of a cell arrive in atomic order
+    and are ranked by index in the reorder kernel)."""
     pos, vel = random_state(50000, seed=11, lo=1.0, hi=4.0, vel_scale=3.0)
-    sim = make(len(pos), key_mode=mode)
+    sim = make(len(pos), key_mode=mode, sort_algo=algo)
+    assert sim.sort_info()["algo"] == ("count" if algo == sph.SPH_SORT_COUNT else "radix")
     sim.set_state(pos, vel)
     sim.simulate()
     prev_ids, _ = sim.get_sorted_index()
@@ -159,6 +166,38 @@ def test_sort_is_stable_across_steps(mode):
         assert np.array_equal(np.sort(ids), np.arange(len(pos), dtype=np.uint32))
         prev_ids = ids
     sim.close()
+
+
+@pytest.mark.parametrize("mode", [sph.SPH_KEY_FLAT, sph.SPH_KEY_MORTON], ids=["flat", "morton"])
+@pytest.mark.parametrize("name", ["random_moving_20k", "compressed_6k", "crowded_cells", "ragged_4097"])
+def test_counting_sort_and_radix_sort_agree_bitwise(name, mode):
+    """The two sorts of the step (SphOptions.sort_algo) give the same order, cell table and -- the
+    summation order being the same -- bit-identical states, step after step.  crowded_cells: 3000
+    particles in a block of 2 x 2 x 2 cells (hundreds of members per cell to rank)."""
+    if name == "crowded_cells":
+        rng = np.random.default_rng(5)
+        pos = (np.float32([3.0, 0.1, 3.0]) + rng.uniform(0, 0.2, (3000, 3))).astype(np.float32)
+        vel = rng.standard_normal((3000, 3)).astype(np.float32)
+    else:
+        pos, vel = STATES[name]()
+    out = []
+    for algo in SORTS:
+        sim = make(len(pos), key_mode=mode, sort_algo=algo)
+        sim.set_state(pos, vel)
+        per_step = []
+        for _ in range(4):
+            sim.simulate()
+            ids, skeys = sim.get_sorted_index()
+            per_step.append((ids, skeys, sim.get_cell_start()))
+        sim.advance(6)    # graph replay
+        per_step.append(sim.get_state())
+        out.append(per_step)
+        sim.close()
+    for a, b in zip(out[0][:-1], out[1][:-1]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(out[0][-1][0], out[1][-1][0])
+    np.testing.assert_array_equal(out[0][-1][1], out[1][-1][1])
 
 
 @pytest.mark.parametrize("name,steps", [("lattice_3d_40k", 40), ("random_30k", 30), ("compressed_6k", 20)])
