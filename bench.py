@@ -544,6 +544,26 @@ def run_ours(args, wl, rank, local_rank, world):
                   "why": "Morton order breaks the 3 x-neighbours of a row into separate runs (27 single-cell runs "
                          "per stencil instead of 9 contiguous x-runs), see profiles/r02_morton_vs_flat.md"}
 
+    # -- the step's sort: the default (counting sort by cell) against the 8-bit radix passes, same run
+    sort_radix = None
+    if sort_info["algo"] == "count" and not args.no_morton:
+        libc.srand(1)
+        sr = sph.Simulator(st, key_mode=key_mode, device=local_rank, sort_algo=sph.SPH_SORT_RADIX)
+        sr.setup()
+        sr.advance(args.warmup)
+        rms = sr.advance_timed(args.steps)
+        sr.profile_enable(True)
+        sr.profile_read(reset=True)
+        sr.advance(prof_steps)
+        rprof = sr.profile_read(reset=True)
+        sr.close()
+        sort_radix = {"ms_per_step": rms / args.steps, "value": n * args.steps / (rms * 1e-3),
+                      "relative_to_default": (rms / args.steps) / (ms / args.steps),
+                      "stages_ms": {k: round(v["ms"] / prof_steps, 4) for k, v in rprof.items()
+                                    if v["launches"] and k in ("histogram", "sort_passes", "reorder_cellstart")},
+                      "default_stages_ms": {k: round(v, 4) for k, v in stage_ms.items()
+                                            if k in ("histogram", "sort_passes", "reorder_cellstart")}}
+
     # -- e2e: same workload through sph_step() with the per-step D2H of positions --------
     def e2e_run(pipeline):
         libc.srand(1)
@@ -665,6 +685,7 @@ def run_ours(args, wl, rank, local_rank, world):
         "roofline": roof,
         "stages": stages,
         "key_morton": morton,
+        "sort_radix": sort_radix,
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
