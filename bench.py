@@ -522,6 +522,7 @@ def run_ours(args, wl, rank, local_rank, world):
     sort_info = sim.sort_info()   # the library says how it sorts: counting sort by cell, or radix passes
     sort_passes = sort_info["radix_passes"]
     prof_steps = max(3, min(10, args.steps))
+    sim.advance(1)   # (the neighbour-count query rebuilt the grid: one step brings the fused count back)
     sim.profile_enable(True)
     sim.profile_read(reset=True)
     sim.advance(prof_steps)
@@ -596,7 +597,8 @@ def run_ours(args, wl, rank, local_rank, world):
         # kernel (+ 8 B tagged pair per particle there) unless it runs as the "histogram" stage (R 4 + W 8)
         sort_bytes = 16 * cells_per_particle + 20
         hist_bytes = 12
-        reorder_bytes = 8 + 8 + 32 + 32 + 12          # pair, cell range, gather, sorted copy, pair-interleaved copy
+        reorder_bytes = 8 + 32 + 32 + 12              # pair, gather, sorted copy, pair-interleaved copy (the cell's
+        #                                               range and members are re-reads of lines the warp already has)
         force_extra = 8 if sort_info["count_fused"] else 0
     else:
         sort_bytes = 4 + 8 + 16 * (passes - 1)
@@ -610,6 +612,8 @@ def run_ours(args, wl, rank, local_rank, world):
     }
     ncu_kernel = {"density": "k_density_flat", "force_integrate": "k_force_integrate_flat",
                   "reorder_cellstart": "k_reorder", "sort_passes": "k_onesweep<0>", "histogram": "k_histogram"}
+    if sort_info["algo"] == "count":
+        ncu_kernel.update({"sort_passes": "k_cell_scatter", "histogram": "k_cell_count"})
 
     def kernel_traffic(stage):   # DRAM bytes per launch of that stage's kernel from the committed ncu capture
         if not traffic or stage not in ncu_kernel:
