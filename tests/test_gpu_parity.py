@@ -200,6 +200,35 @@ def test_counting_sort_and_radix_sort_agree_bitwise(name, mode):
     np.testing.assert_array_equal(out[0][-1][1], out[1][-1][1])
 
 
+def test_state_upload_between_steps_discards_the_fused_count():
+    """The force kernel leaves the next step's per-cell counts behind; a state uploaded between two
+    steps (or a neighbour-count query, which rebuilds the grid) must not see them."""
+    pos1, vel1 = random_state(20000, seed=31, lo=1.0, hi=3.0, vel_scale=2.0)
+    pos2, vel2 = compressed_state(6000, seed=4)
+    pos2 = np.concatenate([pos2, pos1[:14000] + np.float32([4.0, 0.0, 4.0])]).astype(np.float32)
+    vel2 = np.concatenate([vel2, vel1[:14000]]).astype(np.float32)
+    sim = make(len(pos1))
+    sim.set_state(pos1, vel1)
+    sim.advance(3)
+    sim.set_state(pos2, vel2)          # counts of pos1's step 3 are still in the table
+    sim.advance(2)
+    K, C = sim.get_neighbor_counts()   # rebuilds the grid: consumes the counts of step 2
+    sim.advance(2)
+    got = sim.get_state()
+    fresh = make(len(pos2))
+    fresh.set_state(pos2, vel2)
+    fresh.advance(2)
+    K2, C2 = fresh.get_neighbor_counts()
+    fresh.advance(2)
+    want = fresh.get_state()
+    np.testing.assert_array_equal(K, K2)
+    np.testing.assert_array_equal(C, C2)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+    sim.close()
+    fresh.close()
+
+
 @pytest.mark.parametrize("name,steps", [("lattice_3d_40k", 40), ("random_30k", 30), ("compressed_6k", 20)])
 def test_multi_step_aggregates(name, steps):
     """Trajectories diverge chaotically, so after many steps only aggregates are
