@@ -1,17 +1,20 @@
-// sph_sort.cu -- hand-written stable LSD radix sort of (cell key, slot index)
-// pairs for sm_100a: one histogram sweep + one "onesweep" pass per 8-bit digit
-// (chained scan with decoupled look-back, so every pass reads and writes each
-// pair exactly once).
+// sph_sort.cu -- the step's sort of particles by cell key, hand-written for sm_100a.  Two algorithms
+// with the same result, the order (key, position in the array that was sorted):
+//   * counting sort by cell (default; second half of this file): per-cell counts -- taken by the
+//     force kernel of the previous step --, one scan of the cell table, a scatter; the members of a
+//     cell are ranked by index in the reorder kernel.  Every array is read and written once.
+//   * stable LSD radix sort of (cell key, slot index) pairs: one histogram sweep + one "onesweep"
+//     pass per 8-bit digit (chained scan with decoupled look-back, so every pass reads and writes
+//     each pair exactly once).  SPH_SORT=radix / SphOptions.sort_algo; the A/B arm.
 //
 // Replaces the neighbour-search data structures of the three reference variants
 // (ref: src/simulator.cu:44-55 insertList / 133-147 kernelBuildGrid for the
 // lock-free lists; README.md:5 for index_sort and z_index_sort whose source is
-// not mounted).  Stable => the order is deterministic: (key, position in the
-// array that was sorted).
+// not mounted).  Stable => the order is deterministic.
 //
-// Roofline: HBM.  Algorithmic bytes per pair: histogram 4 (keys read once) and
+// Roofline: HBM.  Algorithmic bytes per pair: radix: histogram 4 (keys read once) and
 // per pass 8 read + 8 written (first pass reads only the 4-byte key, the index
-// is implicit).
+// is implicit); counting sort: 32 per particle + 16 per cell (see below).
 #include "sph_sort.cuh"
 #include "sph_common.cuh"
 

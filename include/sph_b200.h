@@ -268,6 +268,9 @@ int sph_debug_flags(sph_sim *sim, uint32_t *flags, int *checked_build);
 /* --- measurement -------------------------------------------------------------
  * Per-kernel CUDA-event times (ms, summed since the last reset) for the stages
  * hash, histogram, sort passes, reorder+cell ranges, density, force+integrate.
+ * With the counting sort by cell (sph_sort_info) "histogram" is the stand-alone count kernel (it
+ * only runs after a state upload; otherwise the count is part of force+integrate) and "sort
+ * passes" are the two table-scan kernels and the scatter.
  * Enabling adds event records around every launch (and disables the graph). */
 #define SPH_STAGE_COUNT 8
 int sph_profile_enable(sph_sim *sim, int on);
