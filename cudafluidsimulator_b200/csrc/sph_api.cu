@@ -64,9 +64,10 @@ struct sph_sim {
     int sm_count = 148;
     int capacity = 0;
     int passes = 0;
-    bool cell_sort = false;     // counting sort by cell instead of the radix passes (single GPU)
-    bool fuse_count = false;    // ... with the count produced by the previous step's force kernel
-    bool counted = false;       // d.cell_count / d.pairs[1] describe the current state (fused count ran)
+    bool cell_sort = false;     // counting sort by cell instead of the radix passes (slabs too: SlabCore)
+    bool fuse_count = false;    // single GPU: ... with the count produced by the previous step's force kernel
+    bool counted = false;       // d.cell_count / d.pairs[1] describe the current state (fused count ran);
+                                // the count table is non-zero exactly while this is set
     int sorted_buf = 0;
     cudaStream_t stream = nullptr;
     float *host_pos = nullptr;  // pinned, 3*n floats, original order
